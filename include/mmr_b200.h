@@ -1,0 +1,183 @@
+/*
+ * mmr_b200.h -- C ABI of the B200-native demagnetization hot path.
+ *
+ * The reference (magpylib-material-response, pure Python) has no FFI layer; the seam this
+ * library fills is what sits underneath its two hot functions:
+ *
+ *   reference call (file:line, relative to /root/reference)            replaced by
+ *   ------------------------------------------------------------------  -----------------------
+ *   3 x magpy.getH(...)   src/magpylib_material_response/demag.py:190,  mmr_assemble
+ *                         :216, :220  (demag_tensor :124-224)
+ *   filter_distance       demag.py:227-277 (max_dist mask)              mmr_assemble (max_dist)
+ *   match_pairs           demag.py:280-321 (pairs_matching dedupe)      mmr_assemble_matched
+ *   T *= mu_0; T.swapaxes(2,3).reshape(3n,3n).T   demag.py:451-452      mmr_assemble (layout)
+ *   Q = np.eye(3n) - np.matmul(S, T)              demag.py:432,:466     mmr_assemble (chi != NULL)
+ *   np.linalg.solve(Q, rhs)                       demag.py:469-470      mmr_lu_factor + mmr_lu_solve
+ *                                                                       or mmr_gmres
+ *   collection.getB(observers) of the solved cells                      mmr_field
+ *       (tests/test_isotropic_anisotropic.py:23, magpylib call)
+ *
+ * Conventions
+ *   - All floating point is FP64.  All pointers named d_* are DEVICE pointers owned by the
+ *     caller (torch tensors); the library allocates only workspace inside the context.
+ *   - Geometry is array-of-structs, row-major: pos[n][3] global cell barycenters (metres),
+ *     quat[n][4] scalar-LAST (x,y,z,w) exactly as scipy Rotation.as_quat() (demag.py:178),
+ *     dim[n][3] full edge lengths.
+ *   - Cell-major ("interleaved") vector/matrix ordering: index 3*cell + component.  The
+ *     reference's component-major ordering (comp*n + cell, demag.py:426-428 order="F") is a
+ *     symmetric permutation of it; the Python host layer converts at the boundary.
+ *   - Matrices are ROW-major with leading dimension ld (in doubles): element (r,c) at
+ *     d_A[r*ld + c]; row r = 3*target + field component, column c = 3*source + polarization
+ *     component.  Rows are what multi-GPU sharding splits ("target-row blocks").
+ *   - Every function returns an int status: 0 ok, <0 invalid argument, >0 a CUDA (1000+code)
+ *     or NCCL (2000+code) error.  Nothing throws across the boundary.  mmr_last_error()
+ *     returns a thread-local message for the last non-zero status.
+ *   - One context per thread/stream; contexts are independent.  All work is enqueued on the
+ *     context's stream; functions that return host scalars synchronize that stream.
+ */
+#ifndef MMR_B200_H
+#define MMR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMR_ABI_VERSION 1
+
+typedef struct mmr_ctx mmr_ctx;
+
+/* layouts for mmr_assemble */
+#define MMR_LAYOUT_CELL_MAJOR 0 /* out[(3*(j-j0)+l)*ld + 3*i+k], dimensionless mu0*H        */
+#define MMR_LAYOUT_REFERENCE 1  /* out[((k*n+i)*n+j)*3+l] = demag.py:224 (3,n,n,3), A/m per T */
+
+/* field selector for mmr_field */
+#define MMR_FIELD_B 0
+#define MMR_FIELD_H 1
+
+int mmr_abi_version(void);
+const char* mmr_last_error(void);
+
+/* ---- context -------------------------------------------------------------------------- */
+/* stream: a cudaStream_t (as void*) or NULL for the legacy default stream. */
+int mmr_ctx_create(int device, void* stream, mmr_ctx** out);
+int mmr_ctx_destroy(mmr_ctx* ctx);
+int mmr_ctx_sync(mmr_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t mmr_ctx_launch_count(mmr_ctx* ctx);
+
+/* ---- kernel 1: demag tensor assembly (demag.py:124-224 + :451-452 + :466) ------------- */
+/*
+ * Evaluates the analytic cuboid H-field block of every source cell i in [src_begin,src_end)
+ * at the barycenter of every target cell j of the target set, for the three global unit
+ * polarizations at once (the 9 entries of a pair share their 6 transcendental terms).
+ *
+ * Target set: block-cyclic over cells -- local target t (0 <= t < n_tgt_local) is global cell
+ *     j = ((t / tgt_block) * tgt_nparts + tgt_part) * tgt_block + t % tgt_block.
+ * Single GPU / contiguous range: tgt_block = n_tgt_local, tgt_nparts = 1, tgt_part = 0 gives
+ * j = t (use tgt_first to offset: j = tgt_first + ...).
+ *
+ * d_chi == NULL : out = N   (N[l,j;k,i] = mu0 * H_l at j for unit J_k of i; inside -> includes -1)
+ * d_chi != NULL : out = I - diag(chi) * N  with chi[3*j+l] (cell-major), i.e. the system matrix Q
+ *                 of demag.py:466 fused into the store.
+ * max_dist != 0 : pairs with |p_j - p_i| / max(dim_i U dim_j) >= max_dist contribute N = 0
+ *                 (evident intent of demag.py:227-277, which raises as written; Appendix A Q2).
+ * layout        : MMR_LAYOUT_CELL_MAJOR (ld >= 3*n doubles, rows are local targets) or
+ *                 MMR_LAYOUT_REFERENCE (d_chi must be NULL, full target range, ld ignored;
+ *                 values divided by mu0 to match demag.py:224 units).
+ */
+int mmr_assemble(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
+                 const double* d_dim, int64_t src_begin, int64_t src_end, int64_t tgt_first,
+                 int64_t n_tgt_local, int64_t tgt_block, int64_t tgt_nparts, int64_t tgt_part,
+                 const double* d_chi, double max_dist, int layout, double* d_out, int64_t ld);
+
+/*
+ * pairs_matching variant (demag.py:280-321): pairs that are equivalent -- same rounded
+ * displacement p_j - p_i (8 decimals after +1e-9, as demag.py:302-304) and same source class
+ * (d_cls[i], host-computed id of the cell's rounded orientation+dimension) -- are evaluated
+ * once (representative = smallest flat index i*n+j, like np.unique's return_index) and copied
+ * to all duplicates.  Output and arguments as mmr_assemble (cell-major only).  n_unique_out
+ * (host pointer, may be NULL) receives the number of unique pairs evaluated.
+ * Returns status -3 if the unique-pair table would exceed table_cap_slots (caller falls back
+ * to mmr_assemble, which produces the same matrix).
+ */
+int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
+                         const double* d_dim, const int32_t* d_cls, const double* d_chi,
+                         double* d_out, int64_t ld, int64_t table_cap_slots,
+                         int64_t* n_unique_out);
+
+/* ---- kernel 2a: dense LU with partial pivoting (np.linalg.solve / dgesv, demag.py:470) -- */
+/*
+ * Factorizes the row-major N x N matrix Q in place.  Pivoting is over COLUMNS of Q (it is
+ * partial pivoting of the column-major view Q^T = P L U), which keeps every pivot search
+ * inside one row block -- the property the multi-GPU row sharding relies on.
+ * d_ipiv: N int32 (device).  info_out (host, may be NULL): 0, or k>0 if pivot k-1 is exactly 0.
+ */
+int mmr_lu_factor(mmr_ctx* ctx, int64_t N, double* d_Q, int64_t ld, int32_t* d_ipiv,
+                  int* info_out);
+/* Solves Q X = B for nrhs right-hand sides; d_B is row-major nrhs x N (each RHS contiguous),
+ * overwritten by the solution. */
+int mmr_lu_solve(mmr_ctx* ctx, int64_t N, const double* d_LU, int64_t ld, const int32_t* d_ipiv,
+                 double* d_B, int64_t nrhs);
+
+/* C = alpha * op(A) op(B) + beta * C on the FP64 tensor-core (DMMA) path used by the LU
+ * trailing update; exported for tests and the roofline measurement.  COLUMN-major (BLAS
+ * convention, "N","N" only): C is m x n, A is m x k, B is k x n. */
+int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* d_A,
+                 int64_t lda, const double* d_B, int64_t ldb, double beta, double* d_C,
+                 int64_t ldc);
+
+/* ---- kernel 2b: restarted GMRES on the same Q with iterative-refinement check ----------- */
+/*
+ * Solves Q x = b (row-major Q, ld).  x holds the initial guess on entry.  Stops when the TRUE
+ * residual ||b - Q x|| / ||b|| (recomputed at every restart = the iterative-refinement
+ * check) <= tol, or after maxit matvecs.  iters_out / relres_out are host pointers.
+ * Returns 0 on convergence, -4 if maxit was reached.
+ */
+int mmr_gmres(mmr_ctx* ctx, int64_t N, const double* d_Q, int64_t ld, const double* d_b,
+              double* d_x, double tol, int restart, int maxit, int* iters_out,
+              double* relres_out);
+
+/* y = Q x for a row block: y[r] = sum_c Q[r*ld + c] x[c], r in [0, nrows). */
+int mmr_matvec(mmr_ctx* ctx, int64_t nrows, int64_t ncols, const double* d_Q, int64_t ld,
+               const double* d_x, double* d_y);
+
+/* ---- field of the (solved) cells at observers (magpylib getB/getH) ---- */
+/* d_pol: [n][3] LOCAL-frame polarizations (tesla); d_obs: [m][3]; d_out: [m][3] global-frame
+ * B (tesla) or H (A/m), summed over all n cells. */
+int mmr_field(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
+              const double* d_dim, const double* d_pol, int64_t m, const double* d_obs,
+              int field, double* d_out);
+
+/* ---- multi-GPU (one process per GPU; NCCL communicator owned by the context) ------------ */
+/* rank 0 calls mmr_nccl_unique_id, the 128-byte id is shipped to the other ranks by the host
+ * (torch.distributed broadcast), then every rank calls mmr_comm_init. */
+int mmr_nccl_unique_id(void* id128_out);
+int mmr_comm_init(mmr_ctx* ctx, const void* id128, int nranks, int rank);
+int mmr_comm_destroy(mmr_ctx* ctx);
+
+/*
+ * Distributed GMRES: this rank owns nrows_local rows of Q (row-major, ld >= N), the rows of the
+ * target set given by (tgt_block, nranks, rank) as in mmr_assemble (row = 3*cell + comp).
+ * d_b and d_x are full-length (N) and replicated; every rank returns the same x.
+ * Per iteration: local row-block matvec, ncclAllGather of the y slices, replicated
+ * orthogonalization (no further collective).
+ */
+int mmr_gmres_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block,
+                   const double* d_Qlocal, int64_t ld, const double* d_b, double* d_x,
+                   double tol, int restart, int maxit, int* iters_out, double* relres_out);
+
+/*
+ * Distributed LU + solve: 1-D block-cyclic over row blocks of Q (= column panels of Q^T) of
+ * width 3*tgt_block; panel factorization is local to the owner, the factored panel and its
+ * pivots are ncclBroadcast, every rank swaps and updates its own panels.  d_b (N, replicated)
+ * is overwritten by the solution on every rank.
+ */
+int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block,
+                      double* d_Qlocal, int64_t ld, double* d_b, int* info_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMR_B200_H */

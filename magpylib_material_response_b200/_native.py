@@ -1,0 +1,330 @@
+"""ctypes binding of libmmr_b200.so (C ABI: include/mmr_b200.h).
+
+PyTorch is used for device memory and streams only; every compute call goes through the
+C ABI with raw device pointers.  There is NO CPU fallback: if the library is missing or no
+B200 is visible, calls raise ``NativeUnavailableError``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import pathlib
+import subprocess
+import threading
+
+_PKG_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG_DIR / "libmmr_b200.so"
+CSRC_DIR = _PKG_DIR / "csrc"
+
+LAYOUT_CELL_MAJOR = 0
+LAYOUT_REFERENCE = 1
+FIELD_B = 0
+FIELD_H = 1
+
+
+class NativeUnavailableError(RuntimeError):
+    """libmmr_b200.so cannot be loaded or no CUDA device is usable."""
+
+
+class NativeError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, status, message):
+        super().__init__(f"libmmr_b200 status {status}: {message}")
+        self.status = status
+
+
+_c_double_p = ctypes.c_void_p  # device pointers travel as integers
+_SIGNATURES = {
+    "mmr_abi_version": (ctypes.c_int, []),
+    "mmr_last_error": (ctypes.c_char_p, []),
+    "mmr_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "mmr_ctx_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mmr_ctx_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "mmr_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mmr_assemble": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]
+        + [ctypes.c_int64] * 7
+        + [_c_double_p, ctypes.c_double, ctypes.c_int, _c_double_p, ctypes.c_int64],
+    ),
+    "mmr_assemble_matched": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p, ctypes.c_void_p,
+         _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
+    ),
+    "mmr_lu_factor": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, ctypes.c_void_p,
+         ctypes.POINTER(ctypes.c_int)],
+    ),
+    "mmr_lu_solve": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, ctypes.c_void_p, _c_double_p,
+         ctypes.c_int64],
+    ),
+    "mmr_dgemm_nn": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, _c_double_p,
+         ctypes.c_int64, _c_double_p, ctypes.c_int64, ctypes.c_double, _c_double_p, ctypes.c_int64],
+    ),
+    "mmr_gmres": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
+         ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+         ctypes.POINTER(ctypes.c_double)],
+    ),
+    "mmr_matvec": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p,
+         _c_double_p],
+    ),
+    "mmr_field": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
+         ctypes.c_int64, _c_double_p, ctypes.c_int, _c_double_p],
+    ),
+    "mmr_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "mmr_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "mmr_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mmr_gmres_dist": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64,
+         _c_double_p, _c_double_p, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+         ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)],
+    ),
+    "mmr_lu_solve_dist": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64,
+         _c_double_p, ctypes.POINTER(ctypes.c_int)],
+    ),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def build(verbose=False):
+    """Compile libmmr_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", str(CSRC_DIR), "-j", str(min(8, os.cpu_count() or 1))]
+    res = subprocess.run(cmd, capture_output=True, text=True, check=False)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        msg = f"building libmmr_b200.so failed (exit {res.returncode})"
+        raise RuntimeError(msg)
+    return LIB_PATH
+
+
+def load_library():
+    """dlopen the C-ABI library and attach prototypes (no GPU needed for this step)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            msg = (
+                f"{LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C magpylib_material_response_b200/csrc`. "
+                "There is no CPU fallback for the demagnetization path."
+            )
+            raise NativeUnavailableError(msg)
+        try:
+            lib = ctypes.CDLL(str(LIB_PATH))
+        except OSError as e:
+            msg = f"cannot load {LIB_PATH}: {e}"
+            raise NativeUnavailableError(msg) from e
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def _check(lib, status):
+    if status != 0:
+        raise NativeError(status, lib.mmr_last_error().decode(errors="replace"))
+
+
+def _ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One C-ABI context = (device, stream).  Thin 1:1 wrapper over the exported functions."""
+
+    def __init__(self, device=0, stream=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            msg = (
+                "No CUDA device is visible: the demagnetization path runs only on a B200 (sm_100a) "
+                "through libmmr_b200.so and has no CPU fallback."
+            )
+            raise NativeUnavailableError(msg)
+        self.lib = load_library()
+        self.torch = torch
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index or 0)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        handle = ctypes.c_void_p()
+        _check(
+            self.lib,
+            self.lib.mmr_ctx_create(
+                self.device.index, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(handle)
+            ),
+        )
+        self.handle = handle
+        self.nranks = 1
+        self.rank = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mmr_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ---------------------------------------------------------------------
+    def to_device(self, arr):
+        import numpy as np
+
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        return t.to(self.device, non_blocking=False)
+
+    def empty(self, *shape, dtype=None):
+        return self.torch.empty(*shape, dtype=dtype or self.torch.float64, device=self.device)
+
+    def sync(self):
+        _check(self.lib, self.lib.mmr_ctx_sync(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mmr_ctx_launch_count(self.handle))
+
+    # ---- kernel 1 --------------------------------------------------------------------
+    def assemble(self, pos, quat, dim, out, ld, *, chi=None, max_dist=0.0, layout=LAYOUT_CELL_MAJOR,
+                 src_range=None, tgt_first=0, n_tgt_local=None, tgt_block=None, tgt_nparts=1,
+                 tgt_part=0):
+        n = pos.shape[0]
+        s0, s1 = src_range if src_range is not None else (0, n)
+        if n_tgt_local is None:
+            n_tgt_local = n
+        if tgt_block is None:
+            tgt_block = max(1, n_tgt_local)
+        _check(
+            self.lib,
+            self.lib.mmr_assemble(
+                self.handle, n, _ptr(pos), _ptr(quat), _ptr(dim), s0, s1, tgt_first, n_tgt_local,
+                tgt_block, tgt_nparts, tgt_part, _ptr(chi), float(max_dist), layout, _ptr(out), ld,
+            ),
+        )
+
+    def assemble_matched(self, pos, quat, dim, cls, out, ld, *, chi=None, table_cap_slots=1 << 24):
+        n = pos.shape[0]
+        nuniq = ctypes.c_int64(0)
+        status = self.lib.mmr_assemble_matched(
+            self.handle, n, _ptr(pos), _ptr(quat), _ptr(dim), _ptr(cls), _ptr(chi), _ptr(out), ld,
+            table_cap_slots, ctypes.byref(nuniq),
+        )
+        if status == -3:
+            return None
+        _check(self.lib, status)
+        return int(nuniq.value)
+
+    # ---- kernel 2a -------------------------------------------------------------------
+    def lu_factor(self, Q, ld, ipiv):
+        info = ctypes.c_int(0)
+        _check(self.lib, self.lib.mmr_lu_factor(self.handle, Q.shape[0], _ptr(Q), ld, _ptr(ipiv),
+                                                ctypes.byref(info)))
+        return info.value
+
+    def lu_solve(self, LU, ld, ipiv, B, nrhs=1):
+        _check(self.lib, self.lib.mmr_lu_solve(self.handle, LU.shape[0], _ptr(LU), ld, _ptr(ipiv),
+                                               _ptr(B), nrhs))
+
+    def dgemm_nn(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+        _check(self.lib, self.lib.mmr_dgemm_nn(self.handle, m, n, k, alpha, _ptr(A), lda, _ptr(B), ldb,
+                                               beta, _ptr(C), ldc))
+
+    # ---- kernel 2b -------------------------------------------------------------------
+    def gmres(self, Q, ld, b, x, tol=1e-10, restart=200, maxit=2000, raise_on_fail=True):
+        iters = ctypes.c_int(0)
+        relres = ctypes.c_double(0.0)
+        status = self.lib.mmr_gmres(self.handle, b.shape[0], _ptr(Q), ld, _ptr(b), _ptr(x), tol, restart,
+                                    maxit, ctypes.byref(iters), ctypes.byref(relres))
+        if status != 0 and (raise_on_fail or status != -4):
+            _check(self.lib, status)
+        return iters.value, relres.value
+
+    def matvec(self, Q, ld, x, y, nrows=None, ncols=None):
+        nrows = Q.shape[0] if nrows is None else nrows
+        ncols = x.shape[0] if ncols is None else ncols
+        _check(self.lib, self.lib.mmr_matvec(self.handle, nrows, ncols, _ptr(Q), ld, _ptr(x), _ptr(y)))
+
+    # ---- field -----------------------------------------------------------------------
+    def field(self, pos, quat, dim, pol, obs, out, field=FIELD_B):
+        _check(self.lib, self.lib.mmr_field(self.handle, pos.shape[0], _ptr(pos), _ptr(quat), _ptr(dim),
+                                            _ptr(pol), obs.shape[0], _ptr(obs), field, _ptr(out)))
+
+    # ---- multi-GPU -------------------------------------------------------------------
+    def comm_init_from_torch(self):
+        """Create the context's NCCL communicator; the 128-byte id is broadcast with
+        torch.distributed (the process group is plumbing only)."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(), dist.get_rank()
+        idbuf = (ctypes.c_char * 128)()
+        if rank == 0:
+            _check(self.lib, self.lib.mmr_nccl_unique_id(ctypes.cast(idbuf, ctypes.c_void_p)))
+        payload = [bytes(idbuf)]
+        dist.broadcast_object_list(payload, src=0)
+        idbuf = ctypes.create_string_buffer(payload[0], 128)
+        _check(self.lib, self.lib.mmr_comm_init(self.handle, ctypes.cast(idbuf, ctypes.c_void_p), world, rank))
+        self.nranks, self.rank = world, rank
+
+    def gmres_dist(self, N, nrows_local, tgt_block, Qlocal, ld, b, x, tol=1e-10, restart=200, maxit=2000):
+        iters = ctypes.c_int(0)
+        relres = ctypes.c_double(0.0)
+        _check(self.lib, self.lib.mmr_gmres_dist(self.handle, N, nrows_local, tgt_block, _ptr(Qlocal), ld,
+                                                 _ptr(b), _ptr(x), tol, restart, maxit,
+                                                 ctypes.byref(iters), ctypes.byref(relres)))
+        return iters.value, relres.value
+
+    def lu_solve_dist(self, N, nrows_local, tgt_block, Qlocal, ld, b):
+        info = ctypes.c_int(0)
+        _check(self.lib, self.lib.mmr_lu_solve_dist(self.handle, N, nrows_local, tgt_block, _ptr(Qlocal),
+                                                    ld, _ptr(b), ctypes.byref(info)))
+        return info.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context per device on torch's current stream."""
+    import torch
+
+    if not torch.cuda.is_available():
+        msg = (
+            "No CUDA device is visible: the demagnetization path runs only on a B200 (sm_100a) "
+            "through libmmr_b200.so and has no CPU fallback."
+        )
+        raise NativeUnavailableError(msg)
+    idx = torch.cuda.current_device() if device is None else int(device)
+    ctx = _default_ctx.get(idx)
+    if ctx is None:
+        ctx = Context(idx, torch.cuda.default_stream(idx))
+        _default_ctx[idx] = ctx
+    return ctx

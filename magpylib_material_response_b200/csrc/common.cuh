@@ -1,0 +1,79 @@
+// Shared context, error plumbing and launch accounting for libmmr_b200.so (see include/mmr_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mmr_b200.h"
+
+#define MMR_PI 3.14159265358979323846
+#define MMR_MU0 1.25663706127e-06  // scipy.constants.mu_0 == magpy.mu_0 (demag.py:451)
+
+struct mmr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // grow-only device workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // second grow-only workspace (LU panels / GMRES basis) so both can be live at once
+  void* ws2 = nullptr;
+  size_t ws2_bytes = 0;
+  // pinned host scratch for small device->host reads
+  void* hpin = nullptr;
+  size_t hpin_bytes = 0;
+  // NCCL (dlopen'ed lazily, comm.cu)
+  void* nccl_comm = nullptr;
+  int nranks = 1;
+  int rank = 0;
+  // side stream + events for look-ahead in the LU
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+void mmr_set_error(const char* fmt, ...);
+int mmr_fail_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define MMR_CUDA(call)                                                 \
+  do {                                                                 \
+    cudaError_t _e = (call);                                           \
+    if (_e != cudaSuccess) return mmr_fail_cuda(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define MMR_CHECK_LAUNCH(ctx)                                          \
+  do {                                                                 \
+    (ctx)->launches++;                                                 \
+    cudaError_t _e = cudaGetLastError();                               \
+    if (_e != cudaSuccess) return mmr_fail_cuda(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+#define MMR_ARG(cond, msg)                          \
+  do {                                              \
+    if (!(cond)) {                                  \
+      mmr_set_error("invalid argument: %s", msg);   \
+      return -1;                                    \
+    }                                               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int mmr_ws_reserve(mmr_ctx* ctx, size_t bytes);    // ctx->ws
+int mmr_ws2_reserve(mmr_ctx* ctx, size_t bytes);   // ctx->ws2
+int mmr_hpin_reserve(mmr_ctx* ctx, size_t bytes);  // ctx->hpin
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

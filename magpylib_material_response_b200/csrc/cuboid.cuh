@@ -1,0 +1,170 @@
+// Analytic field of a homogeneously polarised cuboid -- device functions shared by the
+// assembly kernel (assemble.cu) and the field-evaluation kernel (field.cu).
+//
+// Follows magpylib's published closed form (magnet_cuboid_Bfield / BHJM_magnet_cuboid, the
+// arithmetic underneath the reference's magpy.getH calls at demag.py:190,:216,:220) as stated
+// in SURVEY.md 8a row A3: strict octant folding, the 1e-15 relative surface band, on-edge =>
+// B = 0, inside => subtract J.  The 9 entries of a pair's 3x3 block share 8 sqrt, 6 log-type
+// and 24 atan2 terms, so the block is produced in ONE evaluation (the reference needs three).
+#pragma once
+
+#include "common.cuh"
+
+// Symmetric local-frame block: N[l][k] = mu0 * H_l for unit polarization k (dimensionless).
+struct SymBlock {
+  double xx, yy, zz, xy, xz, yz;
+};
+
+// sum_{corners} sigma * atan2(n_{s2 s3}, d_{s1} * r_{s1 s2 s3}) in the reference's order
+// mmm, pmm, mpm, ppm, mmp, pmp, mpp, ppp with signs + - - + - + + -.
+// (u-,u+) is the axis of the term, (v-,v+), (w-,w+) the two others in the reference's
+// corner-index positions.
+struct Corners {
+  double mmm, pmm, mpm, ppm, mmp, pmp, mpp, ppp;
+};
+
+__device__ __forceinline__ double mmr_atan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ double mmr_log(double x) { return log(x); }
+
+// General (non-special-case) evaluation.  (x,y,z): observer in the source's local frame,
+// (a,b,c): half edge lengths.  `inside` is subtracted from the diagonal (H = (B - J)/mu0).
+__device__ __forceinline__ void cuboid_block_general(double x, double y, double z, double a,
+                                                     double b, double c, double inside,
+                                                     SymBlock& N) {
+  // octant folding, strict inequalities; sign of the off-diagonals is s_k * s_l
+  const double sx = (x < 0.0) ? -1.0 : 1.0;
+  const double sy = (y > 0.0) ? -1.0 : 1.0;
+  const double sz = (z > 0.0) ? -1.0 : 1.0;
+  x = (x < 0.0) ? -x : x;
+  y = (y > 0.0) ? -y : y;
+  z = (z > 0.0) ? -z : z;
+
+  const double xma = x - a, xpa = x + a;
+  const double ymb = y - b, ypb = y + b;
+  const double zmc = z - c, zpc = z + c;
+  const double xma2 = xma * xma, xpa2 = xpa * xpa;
+  const double ymb2 = ymb * ymb, ypb2 = ypb * ypb;
+  const double zmc2 = zmc * zmc, zpc2 = zpc * zpc;
+
+  // r_{s1 s2 s3}; additions in the reference's order (x^2 + y^2) + z^2, no FMA contraction
+  // so that r matches the oracle's sqrt inputs bit for bit.
+  Corners r;
+  r.mmm = sqrt(__dadd_rn(__dadd_rn(xma2, ymb2), zmc2));
+  r.pmm = sqrt(__dadd_rn(__dadd_rn(xpa2, ymb2), zmc2));
+  r.mpm = sqrt(__dadd_rn(__dadd_rn(xma2, ypb2), zmc2));
+  r.ppm = sqrt(__dadd_rn(__dadd_rn(xpa2, ypb2), zmc2));
+  r.mmp = sqrt(__dadd_rn(__dadd_rn(xma2, ymb2), zpc2));
+  r.pmp = sqrt(__dadd_rn(__dadd_rn(xpa2, ymb2), zpc2));
+  r.mpp = sqrt(__dadd_rn(__dadd_rn(xma2, ypb2), zpc2));
+  r.ppp = sqrt(__dadd_rn(__dadd_rn(xpa2, ypb2), zpc2));
+
+  // log terms: numerator corners mmm, ppm, pmp, mpp; denominator pmm, mpm, mmp, ppp
+  const double ff2x =
+      mmr_log((xma + r.mmm) * (xpa + r.ppm) * (xpa + r.pmp) * (xma + r.mpp)) -
+      mmr_log((xpa + r.pmm) * (xma + r.mpm) * (xma + r.mmp) * (xpa + r.ppp));
+  const double ff2y =
+      mmr_log((r.mmm - ymb) * (r.ppm - ypb) * (r.pmp - ymb) * (r.mpp - ypb)) -
+      mmr_log((r.pmm - ymb) * (r.mpm - ypb) * (ymb - r.mmp) * (ypb - r.ppp));
+  const double ff2z =
+      mmr_log((r.mmm - zmc) * (r.ppm - zmc) * (r.pmp - zpc) * (r.mpp - zpc)) -
+      mmr_log((r.pmm - zmc) * (zmc - r.mpm) * (r.mmp - zpc) * (zpc - r.ppp));
+
+  const double yz_mm = ymb * zmc, yz_pm = ypb * zmc, yz_mp = ymb * zpc, yz_pp = ypb * zpc;
+  const double ff1x = mmr_atan2(yz_mm, xma * r.mmm) - mmr_atan2(yz_mm, xpa * r.pmm) -
+                      mmr_atan2(yz_pm, xma * r.mpm) + mmr_atan2(yz_pm, xpa * r.ppm) -
+                      mmr_atan2(yz_mp, xma * r.mmp) + mmr_atan2(yz_mp, xpa * r.pmp) +
+                      mmr_atan2(yz_pp, xma * r.mpp) - mmr_atan2(yz_pp, xpa * r.ppp);
+
+  const double xz_mm = xma * zmc, xz_pm = xpa * zmc, xz_mp = xma * zpc, xz_pp = xpa * zpc;
+  const double ff1y = mmr_atan2(xz_mm, ymb * r.mmm) - mmr_atan2(xz_pm, ymb * r.pmm) -
+                      mmr_atan2(xz_mm, ypb * r.mpm) + mmr_atan2(xz_pm, ypb * r.ppm) -
+                      mmr_atan2(xz_mp, ymb * r.mmp) + mmr_atan2(xz_pp, ymb * r.pmp) +
+                      mmr_atan2(xz_mp, ypb * r.mpp) - mmr_atan2(xz_pp, ypb * r.ppp);
+
+  const double xy_mm = xma * ymb, xy_pm = xpa * ymb, xy_mp = xma * ypb, xy_pp = xpa * ypb;
+  const double ff1z = mmr_atan2(xy_mm, zmc * r.mmm) - mmr_atan2(xy_pm, zmc * r.pmm) -
+                      mmr_atan2(xy_mp, zmc * r.mpm) + mmr_atan2(xy_pp, zmc * r.ppm) -
+                      mmr_atan2(xy_mm, zpc * r.mmp) + mmr_atan2(xy_pm, zpc * r.pmp) +
+                      mmr_atan2(xy_mp, zpc * r.mpp) - mmr_atan2(xy_pp, zpc * r.ppp);
+
+  const double inv4pi = 1.0 / (4.0 * MMR_PI);
+  // G = [[ff1x, ff2z, ff2y], [ff2z, ff1y, -ff2x], [ff2y, -ff2x, ff1z]], F[k][l] = s_k s_l
+  N.xx = ff1x * inv4pi - inside;
+  N.yy = ff1y * inv4pi - inside;
+  N.zz = ff1z * inv4pi - inside;
+  N.xy = ff2z * (sx * sy) * inv4pi;
+  N.xz = ff2y * (sx * sz) * inv4pi;
+  N.yz = -ff2x * (sy * sz) * inv4pi;
+}
+
+// Full evaluation including the special cases of BHJM_magnet_cuboid.
+// If WITH_INSIDE is false the "- J inside" term is left out (that is B, not mu0*H).
+template <bool WITH_INSIDE>
+__device__ __forceinline__ void cuboid_block(double x, double y, double z, double a, double b,
+                                             double c, SymBlock& N) {
+  const double RTOL_SURFACE = 1e-15;
+  a = fabs(a);
+  b = fabs(b);
+  c = fabs(c);
+  const double xd = fabs(x) - a, yd = fabs(y) - b, zd = fabs(z) - c;
+  const bool surf_x = fabs(xd) < RTOL_SURFACE * a;
+  const bool surf_y = fabs(yd) < RTOL_SURFACE * b;
+  const bool surf_z = fabs(zd) < RTOL_SURFACE * c;
+  const bool in_x = xd < RTOL_SURFACE * a;
+  const bool in_y = yd < RTOL_SURFACE * b;
+  const bool in_z = zd < RTOL_SURFACE * c;
+  const bool inside = in_x && in_y && in_z;
+  const bool edge = (surf_y && surf_z && in_x) || (surf_x && surf_z && in_y) ||
+                    (surf_x && surf_y && in_z);
+  const bool dim_null = (a * b * c) == 0.0;
+  const double ins = (WITH_INSIDE && inside) ? 1.0 : 0.0;
+  if (dim_null || edge) {
+    N.xx = N.yy = N.zz = -ins;
+    N.xy = N.xz = N.yz = 0.0;
+    return;
+  }
+  cuboid_block_general(x, y, z, a, b, c, ins, N);
+}
+
+// Rotation matrix from a scalar-last quaternion (x,y,z,w), normalised like scipy does.
+struct Rot3 {
+  double m[9];  // row-major R[r][c]
+};
+
+__device__ __forceinline__ void quat_to_rot(const double* __restrict__ q, Rot3& R) {
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double inv = 1.0 / sqrt(x * x + y * y + z * z + w * w);
+  x *= inv;
+  y *= inv;
+  z *= inv;
+  w *= inv;
+  R.m[0] = 1 - 2 * (y * y + z * z);
+  R.m[1] = 2 * (x * y - z * w);
+  R.m[2] = 2 * (x * z + y * w);
+  R.m[3] = 2 * (x * y + z * w);
+  R.m[4] = 1 - 2 * (x * x + z * z);
+  R.m[5] = 2 * (y * z - x * w);
+  R.m[6] = 2 * (x * z - y * w);
+  R.m[7] = 2 * (y * z + x * w);
+  R.m[8] = 1 - 2 * (x * x + y * y);
+}
+
+// Global-frame 3x3 block G[l][k] = (R N_loc R^T)[l][k]  (H = R H_loc, J_loc = R^T e_k;
+// getBH_level1 frame handling).  out is row-major [l*3+k].
+__device__ __forceinline__ void rotate_block(const Rot3& R, const SymBlock& N, double* out) {
+  // M = N_loc * R^T   (M[a][k] = sum_b N[a][b] R[k][b])
+  double M[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double r0 = R.m[3 * k + 0], r1 = R.m[3 * k + 1], r2 = R.m[3 * k + 2];
+    M[0 * 3 + k] = N.xx * r0 + N.xy * r1 + N.xz * r2;
+    M[1 * 3 + k] = N.xy * r0 + N.yy * r1 + N.yz * r2;
+    M[2 * 3 + k] = N.xz * r0 + N.yz * r1 + N.zz * r2;
+  }
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      out[l * 3 + k] = R.m[3 * l + 0] * M[0 * 3 + k] + R.m[3 * l + 1] * M[1 * 3 + k] +
+                       R.m[3 * l + 2] * M[2 * 3 + k];
+}

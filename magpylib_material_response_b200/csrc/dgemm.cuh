@@ -1,0 +1,180 @@
+// FP64 GEMM on the tensor-core DMMA path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4 on sm_100a;
+// tcgen05 has no FP64 kind and wgmma is sm_90a-only).  This is the trailing-update engine of
+// the blocked LU (the ~2/3 N^3 flops of np.linalg.solve, demag.py:470).
+//
+//   C (m x n) = alpha * A (m x k) * B (k x n) + beta * C      column-major, "N","N"
+//
+// CTA tile 128 x 64, BK = 16, 8 warps (4 along m x 2 along n), warp tile 32 x 32 = 4 x 4 DMMA
+// fragments (32 FP64 accumulators per thread), 3-stage cp.async pipeline, 2 CTAs per SM so one
+// CTA's C read-modify-write epilogue overlaps the other's main loop.  Shared-memory rows are
+// padded by 4 doubles so that both fragment load patterns are bank-conflict free.
+#pragma once
+
+#include "common.cuh"
+
+namespace mmr_gemm {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, THREADS = 256;
+constexpr int LDA_S = BM + 4;  // doubles per k-row of the A stage   ((k*132 + m) mod 16 distinct)
+constexpr int LDB_S = BK + 4;  // doubles per n-row of the B stage   ((n*20 + k) mod 16 distinct)
+constexpr int A_STAGE = BK * LDA_S;
+constexpr int B_STAGE = BN * LDB_S;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// ALIGNED16: A, B 16-byte aligned with even leading dimensions (cp.async 16 B); otherwise 8 B.
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(THREADS, 2)
+    dgemm_nn_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
+                    const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
+                    int64_t ldc) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wm = warp & 3;   // 4 warps along m
+  const int wn = warp >> 2;  // 2 warps along n
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = (k + BK - 1) / BK;
+
+  auto load_tile = [&](int stage, int kt) {
+    const int k0 = kt * BK;
+    double* as = As + stage * A_STAGE;
+    double* bs = Bs + stage * B_STAGE;
+    if (ALIGNED16) {
+      // A: 16 k-rows x 64 chunks of 2 doubles
+#pragma unroll
+      for (int it = 0; it < (BK * BM / 2) / THREADS; ++it) {
+        const int idx = tid + it * THREADS;
+        const int kr = idx / (BM / 2);
+        const int mc = (idx % (BM / 2)) * 2;
+        const int gm = m0 + mc, gk = k0 + kr;
+        int bytes = 0;
+        if (gk < k && gm < m) bytes = (m - gm >= 2) ? 16 : 8;
+        const double* src = bytes ? (A + (int64_t)gk * lda + gm) : A;
+        cp_async16(as + kr * LDA_S + mc, src, bytes);
+      }
+      // B: 64 n-rows x 8 chunks of 2 doubles
+#pragma unroll
+      for (int it = 0; it < (BN * BK / 2) / THREADS; ++it) {
+        const int idx = tid + it * THREADS;
+        const int nr = idx / (BK / 2);
+        const int kc = (idx % (BK / 2)) * 2;
+        const int gn = n0 + nr, gk = k0 + kc;
+        int bytes = 0;
+        if (gn < n && gk < k) bytes = (k - gk >= 2) ? 16 : 8;
+        const double* src = bytes ? (B + (int64_t)gn * ldb + gk) : B;
+        cp_async16(bs + nr * LDB_S + kc, src, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < (BK * BM) / THREADS; ++it) {
+        const int idx = tid + it * THREADS;
+        const int kr = idx / BM;
+        const int mc = idx % BM;
+        const int gm = m0 + mc, gk = k0 + kr;
+        const bool ok = (gk < k && gm < m);
+        cp_async8(as + kr * LDA_S + mc, ok ? (A + (int64_t)gk * lda + gm) : A, ok ? 8 : 0);
+      }
+#pragma unroll
+      for (int it = 0; it < (BN * BK) / THREADS; ++it) {
+        const int idx = tid + it * THREADS;
+        const int nr = idx / BK;
+        const int kc = idx % BK;
+        const int gn = n0 + nr, gk = k0 + kc;
+        const bool ok = (gn < n && gk < k);
+        cp_async8(bs + nr * LDB_S + kc, ok ? (B + (int64_t)gn * ldb + gk) : B, ok ? 8 : 0);
+      }
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_tile(s, s);
+    cp_async_commit();
+  }
+
+  const int a_row = wm * 32 + (lane >> 2);  // + 8*f
+  const int b_row = wn * 32 + (lane >> 2);  // + 8*g
+  const int kq = lane & 3;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < KT) load_tile(nxt % STAGES, nxt);
+    cp_async_commit();
+
+    const double* as = As + (kt % STAGES) * A_STAGE;
+    const double* bs = Bs + (kt % STAGES) * B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) af[f] = as[(kk + kq) * LDA_S + a_row + 8 * f];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) bf[g] = bs[(b_row + 8 * g) * LDB_S + kk + kq];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dmma884(acc[f][g][0], acc[f][g][1], af[f], bf[g]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread holds rows (lane>>2), cols 2*(lane&3) + {0,1} of each 8x8 fragment
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const int gm = m0 + wm * 32 + 8 * f + (lane >> 2);
+    if (gm >= m) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
+        if (gn < n) {
+          double* cp = C + (int64_t)gn * ldc + gm;
+          const double v = alpha * acc[f][g][e];
+          *cp = (beta == 0.0) ? v : (v + beta * (*cp));
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mmr_gemm
+
+// host-side launcher (defined in lu.cu)
+int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                     double* C, int64_t ldc);

@@ -1,0 +1,595 @@
+// Kernel 2a: dense LU with partial pivoting + triangular solves -- replaces
+// np.linalg.solve(Q, rhs) (LAPACK dgesv) of demag.py:469-470.
+//
+// Storage trick: Q is row-major (rows = target cells, the multi-GPU sharding unit).  Its memory
+// is, verbatim, the column-major matrix A = Q^T.  We run a textbook right-looking blocked LU with
+// partial (row) pivoting on that column-major view, A = P L U, and solve Q x = b through
+// Q = A^T = U^T L^T P^T.  Every pivot search then stays inside one column panel of A = one
+// row block of Q = one GPU, which is what the 1-D block-cyclic distribution needs.
+//
+// Per panel of NB columns:
+//   strips of W columns:  cooperative "strip" kernel (panel rows spread over all SMs in shared
+//                         memory, one grid barrier per column for the pivot search)
+//                         -> swaps + W x W triangular solve on the rest of the panel
+//                         -> rank-W DMMA update of the rest of the panel
+//   row swaps on the columns outside the panel, TRSM (U12 = L11^-1 A12), DMMA trailing update.
+#include <cooperative_groups.h>
+
+#include "dgemm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NB = 128;  // panel width
+constexpr int W = 16;    // strip width inside the panel
+constexpr int STRIP_THREADS = 256;
+constexpr int MIN_ROWS_PER_CTA = 64;
+
+struct Cand {
+  double absval;
+  int row;
+  int pad;
+};
+
+// ---------------------------------------------------------------------------------------
+// Strip factorization: columns [c0, c0+w) (w <= W), rows [c0, N) of column-major A.
+// Rows are split into contiguous chunks, one per CTA, held in shared memory for the whole
+// strip.  CTA 0 owns the top W rows.  One grid barrier per column.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STRIP_THREADS)
+    lu_strip_kernel(double* __restrict__ A, int64_t ld, int N, int c0, int w, int rows_per,
+                    int* __restrict__ ipiv, Cand* __restrict__ cand, double* __restrict__ candrow,
+                    double* __restrict__ diagrow, int* __restrict__ info) {
+  extern __shared__ __align__(16) double S[];  // [W][rows_per]
+  __shared__ double s_red_val[STRIP_THREADS / 32];
+  __shared__ int s_red_row[STRIP_THREADS / 32];
+  __shared__ double s_prow[W];
+  __shared__ int s_piv_row;
+  __shared__ int s_piv_cta;
+
+  cg::grid_group grid = cg::this_grid();
+  const int G = gridDim.x;
+  const int cta = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int m = N - c0;
+  const int r_begin = cta * rows_per;                // local (panel-relative) first row
+  const int r_cnt = max(0, min(rows_per, m - r_begin));
+
+  // load chunk: S[c*rows_per + r] = A[(c0 + r_begin + r) + (c0 + c)*ld]
+  for (int c = 0; c < w; ++c) {
+    const double* src = A + (int64_t)(c0 + c) * ld + c0 + r_begin;
+    for (int r = tid; r < r_cnt; r += STRIP_THREADS) S[c * rows_per + r] = src[r];
+  }
+  __syncthreads();
+
+  for (int jj = 0; jj < w; ++jj) {
+    const int buf = jj & 1;
+    // 1. local argmax over rows with panel-relative index >= jj
+    double best = -1.0;
+    int best_row = 0x7fffffff;
+    {
+      const int lo = max(0, jj - r_begin);
+      for (int r = lo + tid; r < r_cnt; r += STRIP_THREADS) {
+        const double v = fabs(S[jj * rows_per + r]);
+        if (v > best) {  // strict: first maximum wins inside a thread (rows ascending)
+          best = v;
+          best_row = r_begin + r;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int orow = __shfl_down_sync(0xffffffffu, best_row, off);
+        if (ov > best || (ov == best && orow < best_row)) {
+          best = ov;
+          best_row = orow;
+        }
+      }
+      if ((tid & 31) == 0) {
+        s_red_val[tid >> 5] = best;
+        s_red_row[tid >> 5] = best_row;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int q = 1; q < STRIP_THREADS / 32; ++q) {
+          if (s_red_val[q] > best || (s_red_val[q] == best && s_red_row[q] < best_row)) {
+            best = s_red_val[q];
+            best_row = s_red_row[q];
+          }
+        }
+        Cand cd;
+        cd.absval = best;
+        cd.row = best_row;
+        cd.pad = 0;
+        cand[buf * G + cta] = cd;
+        s_piv_row = best_row;  // local candidate, reused below to publish the row
+      }
+      __syncthreads();
+      // publish my candidate row (w values) and, from CTA 0, the current diagonal row
+      if (best >= 0.0 || true) {
+        const int lr = s_piv_row - r_begin;
+        if (tid < w && s_piv_row != 0x7fffffff && lr >= 0 && lr < r_cnt)
+          candrow[((int64_t)buf * G + cta) * W + tid] = S[tid * rows_per + lr];
+      }
+      if (cta == 0 && tid < w) diagrow[buf * W + tid] = S[tid * rows_per + jj];
+    }
+    __threadfence();
+    grid.sync();
+
+    // 2. every CTA picks the winner redundantly
+    if (tid < 32) {
+      double bv = -1.0;
+      int br = 0x7fffffff, bc = 0;
+      for (int q = tid; q < G; q += 32) {
+        const Cand cd = cand[buf * G + q];
+        if (cd.absval > bv || (cd.absval == bv && cd.row < br)) {
+          bv = cd.absval;
+          br = cd.row;
+          bc = q;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int orow = __shfl_down_sync(0xffffffffu, br, off);
+        const int oc = __shfl_down_sync(0xffffffffu, bc, off);
+        if (ov > bv || (ov == bv && orow < br)) {
+          bv = ov;
+          br = orow;
+          bc = oc;
+        }
+      }
+      if (tid == 0) {
+        s_piv_row = br;
+        s_piv_cta = bc;
+      }
+    }
+    __syncthreads();
+    const int prow = s_piv_row;  // panel-relative pivot row
+    const int pcta = s_piv_cta;
+    if (tid < w) s_prow[tid] = candrow[((int64_t)buf * G + pcta) * W + tid];
+    __syncthreads();
+    // 3. swap: pivot row <- old diagonal row (owner of prow); diagonal row <- pivot row (CTA 0)
+    if (prow != jj) {
+      if (cta == pcta && tid < w) {
+        const double dv = diagrow[buf * W + tid];
+        S[tid * rows_per + (prow - r_begin)] = dv;
+      }
+      __syncthreads();  // if pcta == 0 the two writes touch different rows; order is irrelevant
+      if (cta == 0 && tid < w) S[tid * rows_per + jj] = s_prow[tid];
+    }
+    if (cta == 0 && tid == 0) {
+      ipiv[c0 + jj] = c0 + prow;
+      if (s_prow[jj] == 0.0) atomicCAS(info, 0, c0 + jj + 1);
+    }
+    __syncthreads();
+    // 4. scale column jj and rank-1 update of the strip columns to its right
+    const double piv = s_prow[jj];
+    if (piv != 0.0) {
+      const double rinv = 1.0 / piv;
+      const int lo = max(0, jj + 1 - r_begin);
+      for (int r = lo + tid; r < r_cnt; r += STRIP_THREADS) {
+        const double l = S[jj * rows_per + r] * rinv;
+        S[jj * rows_per + r] = l;
+        for (int c = jj + 1; c < w; ++c) S[c * rows_per + r] -= l * s_prow[c];
+      }
+    }
+    __syncthreads();
+  }
+
+  // write back
+  for (int c = 0; c < w; ++c) {
+    double* dst = A + (int64_t)(c0 + c) * ld + c0 + r_begin;
+    for (int r = tid; r < r_cnt; r += STRIP_THREADS) dst[r] = S[c * rows_per + r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// After a strip [c0, c0+w) is factored: apply its row swaps to the other panel columns
+// [pc0, c0) and [c0+w, pc1), and for the right part also solve with the strip's unit-lower
+// W x W block (rows c0..c0+w of those columns become rows of U).  One thread per column.
+// ---------------------------------------------------------------------------------------
+__global__ void lu_panel_swap_trsm_kernel(double* __restrict__ A, int64_t ld, int c0, int w, int pc0,
+                                          int pc1, const int* __restrict__ ipiv) {
+  __shared__ double L[W][W + 1];
+  __shared__ int piv[W];
+  const int tid = threadIdx.x;
+  if (tid < w) piv[tid] = ipiv[c0 + tid];
+  for (int e = tid; e < w * w; e += blockDim.x) {
+    const int r = e % w, c = e / w;
+    L[r][c] = A[(int64_t)(c0 + c) * ld + c0 + r];
+  }
+  __syncthreads();
+  const int ncol_left = c0 - pc0;
+  const int ncol = ncol_left + (pc1 - (c0 + w));
+  for (int t = blockIdx.x * blockDim.x + tid; t < ncol; t += gridDim.x * blockDim.x) {
+    const bool right = t >= ncol_left;
+    const int col = right ? (c0 + w + (t - ncol_left)) : (pc0 + t);
+    double* a = A + (int64_t)col * ld;
+    for (int i = 0; i < w; ++i) {
+      const int p = piv[i];
+      if (p != c0 + i) {
+        const double tmp = a[c0 + i];
+        a[c0 + i] = a[p];
+        a[p] = tmp;
+      }
+    }
+    if (right) {
+      double x[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) x[i] = (i < w) ? a[c0 + i] : 0.0;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+#pragma unroll
+        for (int q = 0; q < i; ++q) x[i] -= L[i][q] * x[q];
+      }
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (i < w) a[c0 + i] = x[i];
+    }
+  }
+}
+
+// Row swaps ipiv[k0..k1) applied to columns [col_begin, col_end): one thread per column.
+__global__ void lu_laswp_kernel(double* __restrict__ A, int64_t ld, int k0, int k1, int col_begin,
+                                int col_end, const int* __restrict__ ipiv) {
+  extern __shared__ int s_piv[];
+  for (int i = threadIdx.x; i < k1 - k0; i += blockDim.x) s_piv[i] = ipiv[k0 + i];
+  __syncthreads();
+  const int col = col_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= col_end) return;
+  double* a = A + (int64_t)col * ld;
+  for (int i = 0; i < k1 - k0; ++i) {
+    const int p = s_piv[i];
+    if (p != k0 + i) {
+      const double tmp = a[k0 + i];
+      a[k0 + i] = a[p];
+      a[p] = tmp;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// TRSM: B (nb x ncols, column-major, ldb) <- L^-1 B with L = unit lower nb x nb block of the
+// factored panel (column-major, ldl).  One CTA per TRSM_COLS columns of B, B block in shared
+// memory, rows resolved in order with the multipliers read through L1/L2.
+// ---------------------------------------------------------------------------------------
+constexpr int TRSM_COLS = 32;
+
+__global__ void __launch_bounds__(256)
+    lu_trsm_kernel(const double* __restrict__ L, int64_t ldl, int nb, double* __restrict__ B,
+                   int64_t ldb, int ncols) {
+  extern __shared__ __align__(16) double sm[];
+  double* Bs = sm;                       // [TRSM_COLS][nb+1]
+  double* Ls = sm + TRSM_COLS * (nb + 1);  // [nb][nb+1] column-major with padding: Ls[c*(nb+1)+r]
+  const int tid = threadIdx.x;
+  const int cb = blockIdx.x * TRSM_COLS;
+  const int nc = min(TRSM_COLS, ncols - cb);
+  for (int e = tid; e < nc * nb; e += blockDim.x) {
+    const int r = e % nb, c = e / nb;
+    Bs[c * (nb + 1) + r] = B[(int64_t)(cb + c) * ldb + r];
+  }
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    const int r = e % nb, c = e / nb;
+    Ls[c * (nb + 1) + r] = (r > c) ? L[(int64_t)c * ldl + r] : 0.0;
+  }
+  __syncthreads();
+  // thread -> (column c = tid % TRSM_COLS, row group rg = tid / TRSM_COLS of 8 groups)
+  const int c = tid % TRSM_COLS;
+  const int rg = tid / TRSM_COLS;
+  constexpr int RG = 256 / TRSM_COLS;
+  for (int t = 0; t < nb - 1; ++t) {
+    const double bt = Bs[c * (nb + 1) + t];
+    if (c < nc) {
+      for (int r = t + 1 + rg; r < nb; r += RG) Bs[c * (nb + 1) + r] -= Ls[t * (nb + 1) + r] * bt;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < nc * nb; e += blockDim.x) {
+    const int r = e % nb, cc = e / nb;
+    B[(int64_t)(cb + cc) * ldb + r] = Bs[cc * (nb + 1) + r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Triangular solves for Q x = b with Q^T = A = P L U:  U^T w = b,  L^T v = w,  x = P v.
+// Each "row" of U^T / L^T is a contiguous column of A, so the off-diagonal part is a
+// coalesced dot-product GEMV (one warp per column), the diagonal block a small serial solve.
+// ---------------------------------------------------------------------------------------
+constexpr int SB = 128;  // diagonal block of the triangular solves
+
+// b[c] -= sum_{r in [r0,r1)} A[r + c*ld] * x[r]   for c in [c_begin, c_end); one warp per column
+__global__ void __launch_bounds__(256)
+    lu_gemv_t_kernel(const double* __restrict__ A, int64_t ld, int r0, int r1, int c_begin,
+                     int c_end, const double* x, double* b) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c = c_begin + warp;
+  if (c >= c_end) return;
+  const double* a = A + (int64_t)c * ld;
+  double acc = 0.0;
+  for (int r = r0 + lane; r < r1; r += 32) acc += a[r] * x[r];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if (lane == 0) b[c] -= acc;
+}
+
+// Solve the SB x SB diagonal block in place (single CTA of SB threads, block transposed into
+// dynamic shared memory).
+//   UPPER_T: w[c] = (b[c] - sum_{k0<=r<c} A[r,c] w[r]) / A[c,c]      ascending c
+//   else   : v[c] =  b[c] - sum_{c<r<k1} A[r,c] v[r]                 descending c (unit diag)
+template <bool UPPER_T>
+__global__ void __launch_bounds__(SB)
+    lu_diag_solve_kernel(const double* __restrict__ A, int64_t ld, int k0, int k1,
+                         double* __restrict__ b) {
+  extern __shared__ __align__(16) double T[];  // T[r*(SB+1) + c] = A[k0+r, k0+c]
+  __shared__ double x[SB];
+  const int tid = threadIdx.x;
+  const int nbk = k1 - k0;
+  for (int c = 0; c < nbk; ++c) {
+    if (tid < nbk) T[tid * (SB + 1) + c] = A[(int64_t)(k0 + c) * ld + k0 + tid];
+  }
+  if (tid < nbk) x[tid] = b[k0 + tid];
+  __syncthreads();
+  if (UPPER_T) {
+    for (int r = 0; r < nbk; ++r) {
+      if (tid == r) x[r] = x[r] / T[r * (SB + 1) + r];
+      __syncthreads();
+      if (tid > r && tid < nbk) x[tid] -= T[r * (SB + 1) + tid] * x[r];
+      __syncthreads();
+    }
+  } else {
+    for (int r = nbk - 1; r >= 0; --r) {
+      if (tid < r) x[tid] -= T[r * (SB + 1) + tid] * x[r];
+      __syncthreads();
+    }
+  }
+  if (tid < nbk) b[k0 + tid] = x[tid];
+}
+
+__global__ void lu_gather_kernel(const double* __restrict__ v, const int* __restrict__ perm, int N,
+                                 double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) x[i] = v[perm[i]];
+}
+
+}  // namespace
+
+int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                     double* C, int64_t ldc) {
+  using namespace mmr_gemm;
+  if (m <= 0 || n <= 0) return 0;
+  static bool attr_set[2] = {false, false};
+  const bool aligned = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
+  if (!attr_set[aligned]) {
+    if (aligned)
+      MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)SMEM_BYTES));
+    else
+      MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)SMEM_BYTES));
+    attr_set[aligned] = true;
+  }
+  dim3 grid((unsigned)ceil_div64(m, BM), (unsigned)ceil_div64(n, BN));
+  if (aligned)
+    dgemm_nn_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb,
+                                                           beta, C, ldc);
+  else
+    dgemm_nn_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B,
+                                                            ldb, beta, C, ldc);
+  MMR_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+extern "C" int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
+                            const double* d_A, int64_t lda, const double* d_B, int64_t ldb,
+                            double beta, double* d_C, int64_t ldc) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(m >= 0 && n >= 0 && k >= 0, "negative size");
+  MMR_ARG(m < (1LL << 31) && n < (1LL << 31) && k < (1LL << 31), "size exceeds int32");
+  MMR_ARG(lda >= m && ldb >= k && ldc >= m, "leading dimension too small");
+  DeviceGuard g(ctx->device);
+  return mmr_dgemm_launch(ctx, ctx->stream, m, n, k, alpha, d_A, lda, d_B, ldb, beta, d_C, ldc);
+}
+
+// Factor the panel columns [kb, kb+nb) rows [kb, N) of column-major A (local pointer/ld), pivots
+// into d_ipiv[kb..kb+nb) (global row indices).  Used by the single-GPU and distributed drivers.
+int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
+                 int* d_info, void* d_scratch) {
+  static int max_coop_ctas = -1;
+  static size_t strip_smem_cap = 0;
+  if (max_coop_ctas < 0) {
+    strip_smem_cap = 200 * 1024;
+    MMR_CUDA(cudaFuncSetAttribute(lu_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)strip_smem_cap));
+    max_coop_ctas = ctx->sm_count;  // 1 CTA per SM at up to 200 KB of shared memory
+  }
+  Cand* cand = (Cand*)d_scratch;
+  double* candrow = (double*)((char*)d_scratch + 2 * 256 * sizeof(Cand));
+  double* diagrow = candrow + 2 * 256 * W;
+  for (int c0 = kb; c0 < kb + nb; c0 += W) {
+    const int w = min(W, kb + nb - c0);
+    const int m = N - c0;
+    int G = min(max_coop_ctas, max(1, m / MIN_ROWS_PER_CTA));
+    int rows_per = (int)ceil_div64(m, G);
+    rows_per = max(rows_per, W);
+    rows_per = (rows_per + 1) & ~1;
+    G = (int)ceil_div64(m, rows_per);
+    const size_t smem = (size_t)W * rows_per * sizeof(double);
+    if (smem > strip_smem_cap) {
+      mmr_set_error("LU strip of %d rows does not fit the distributed shared memory (%zu B/CTA)", m, smem);
+      return -5;
+    }
+    int w_arg = w, N_arg = N, c0_arg = c0;
+    void* args[] = {&A, &ld, &N_arg, &c0_arg, &w_arg, &rows_per, &d_ipiv, &cand, &candrow, &diagrow, &d_info};
+    MMR_CUDA(cudaLaunchCooperativeKernel((void*)lu_strip_kernel, dim3(G), dim3(STRIP_THREADS), args, smem,
+                                         ctx->stream));
+    ctx->launches++;
+    const int ncol_other = nb - w;
+    if (ncol_other > 0) {
+      lu_panel_swap_trsm_kernel<<<1, 128, 0, ctx->stream>>>(A, ld, c0, w, kb, kb + nb, d_ipiv);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+    const int nright = kb + nb - (c0 + w);
+    const int mbelow = N - (c0 + w);
+    if (nright > 0 && mbelow > 0) {
+      int rc = mmr_dgemm_launch(ctx, ctx->stream, mbelow, nright, w, -1.0,
+                                A + (int64_t)c0 * ld + (c0 + w), ld,
+                                A + (int64_t)(c0 + w) * ld + c0, ld, 1.0,
+                                A + (int64_t)(c0 + w) * ld + (c0 + w), ld);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+size_t mmr_lu_panel_scratch_bytes() { return 2 * 256 * sizeof(Cand) + (2 * 256 * W + 2 * W) * sizeof(double); }
+
+int mmr_lu_laswp(mmr_ctx* ctx, double* A, int64_t ld, int k0, int k1, int col_begin, int col_end,
+                 const int* d_ipiv) {
+  if (col_end <= col_begin || k1 <= k0) return 0;
+  const int threads = 128;
+  lu_laswp_kernel<<<(unsigned)ceil_div64(col_end - col_begin, threads), threads, (k1 - k0) * sizeof(int),
+                    ctx->stream>>>(A, ld, k0, k1, col_begin, col_end, d_ipiv);
+  MMR_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int mmr_lu_trsm(mmr_ctx* ctx, const double* L, int64_t ldl, int nb, double* B, int64_t ldb, int ncols) {
+  if (ncols <= 0 || nb <= 0) return 0;
+  const size_t smem = ((size_t)TRSM_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
+  static size_t cap = 0;
+  if (smem > cap) {
+    MMR_CUDA(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cap = smem;
+  }
+  lu_trsm_kernel<<<(unsigned)ceil_div64(ncols, TRSM_COLS), 256, smem, ctx->stream>>>(L, ldl, nb, B, ldb, ncols);
+  MMR_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld, int32_t* d_ipiv,
+                             int* info_out) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(N64 >= 0 && N64 < (1LL << 31), "N out of range");
+  MMR_ARG(ld >= N64, "ld must be >= N");
+  if (info_out) *info_out = 0;
+  if (N64 == 0) return 0;
+  MMR_ARG(d_Q && d_ipiv, "NULL matrix/pivot pointer");
+  DeviceGuard g(ctx->device);
+  const int N = (int)N64;
+  int rc = mmr_ws_reserve(ctx, 256 + mmr_lu_panel_scratch_bytes());
+  if (rc) return rc;
+  rc = mmr_hpin_reserve(ctx, 256);
+  if (rc) return rc;
+  int* d_info = (int*)ctx->ws;
+  void* scratch = (char*)ctx->ws + 256;
+  MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+  double* A = d_Q;
+  for (int kb = 0; kb < N; kb += NB) {
+    const int nb = min(NB, N - kb);
+    rc = mmr_lu_panel(ctx, A, ld, N, kb, nb, d_ipiv, d_info, scratch);
+    if (rc) return rc;
+    // swaps on the columns left and right of the panel
+    rc = mmr_lu_laswp(ctx, A, ld, kb, kb + nb, 0, kb, d_ipiv);
+    if (rc) return rc;
+    const int ntrail = N - (kb + nb);
+    if (ntrail > 0) {
+      rc = mmr_lu_laswp(ctx, A, ld, kb, kb + nb, kb + nb, N, d_ipiv);
+      if (rc) return rc;
+      // U12 = L11^-1 A12
+      rc = mmr_lu_trsm(ctx, A + (int64_t)kb * ld + kb, ld, nb, A + (int64_t)(kb + nb) * ld + kb, ld, ntrail);
+      if (rc) return rc;
+      // A22 -= L21 U12
+      rc = mmr_dgemm_launch(ctx, ctx->stream, ntrail, ntrail, nb, -1.0, A + (int64_t)kb * ld + (kb + nb), ld,
+                            A + (int64_t)(kb + nb) * ld + kb, ld, 1.0,
+                            A + (int64_t)(kb + nb) * ld + (kb + nb), ld);
+      if (rc) return rc;
+    }
+  }
+  MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info_out) *info_out = *(int*)ctx->hpin;
+  return 0;
+}
+
+// U^T w = b (forward) then L^T v = w (backward), in place on d_b (length N).  Right-looking:
+// as soon as a diagonal block of the solution is final it is eliminated from ALL remaining
+// equations at once (one warp per remaining column, SB-long contiguous dot products).
+int mmr_lu_tri_solves(mmr_ctx* ctx, int N, const double* A, int64_t ld, double* d_b) {
+  static bool attr = false;
+  const size_t smem = (size_t)SB * (SB + 1) * sizeof(double);
+  if (!attr) {
+    MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  for (int k0 = 0; k0 < N; k0 += SB) {
+    const int k1 = min(N, k0 + SB);
+    lu_diag_solve_kernel<true><<<1, SB, smem, ctx->stream>>>(A, ld, k0, k1, d_b);
+    MMR_CHECK_LAUNCH(ctx);
+    if (k1 < N) {
+      lu_gemv_t_kernel<<<(unsigned)ceil_div64((int64_t)(N - k1) * 32, 256), 256, 0, ctx->stream>>>(
+          A, ld, k0, k1, k1, N, d_b, d_b);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+  }
+  const int nblk = (int)ceil_div64(N, SB);
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int k0 = blk * SB;
+    const int k1 = min(N, k0 + SB);
+    lu_diag_solve_kernel<false><<<1, SB, smem, ctx->stream>>>(A, ld, k0, k1, d_b);
+    MMR_CHECK_LAUNCH(ctx);
+    if (k0 > 0) {
+      lu_gemv_t_kernel<<<(unsigned)ceil_div64((int64_t)k0 * 32, 256), 256, 0, ctx->stream>>>(
+          A, ld, k0, k1, 0, k0, d_b, d_b);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+  }
+  return 0;
+}
+
+extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64_t ld,
+                            const int32_t* d_ipiv, double* d_B, int64_t nrhs) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(N64 >= 0 && N64 < (1LL << 31), "N out of range");
+  MMR_ARG(ld >= N64 && nrhs >= 0, "bad ld/nrhs");
+  if (N64 == 0 || nrhs == 0) return 0;
+  MMR_ARG(d_LU && d_ipiv && d_B, "NULL pointer");
+  DeviceGuard g(ctx->device);
+  const int N = (int)N64;
+  // permutation from the pivot sequence, on the host: x = P v, P = S_0 S_1 ... S_{N-1}
+  int rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
+  if (rc) return rc;
+  rc = mmr_ws_reserve(ctx, sizeof(int) * (size_t)N + sizeof(double) * (size_t)N + 512);
+  if (rc) return rc;
+  int* h_ipiv = (int*)ctx->hpin;
+  int* h_perm = h_ipiv + N;
+  MMR_CUDA(cudaMemcpyAsync(h_ipiv, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < N; ++i) h_perm[i] = i;
+  for (int i = N - 1; i >= 0; --i) {
+    const int p = h_ipiv[i];
+    if (p != i) {
+      const int t = h_perm[i];
+      h_perm[i] = h_perm[p];
+      h_perm[p] = t;
+    }
+  }
+  // after the loop x[h_perm^-1...]: we applied the swaps to an index array idx (idx = P applied
+  // to identity positions), so x[i] = v[idx[i]].
+  int* d_perm = (int*)ctx->ws;
+  double* d_tmp = (double*)((char*)ctx->ws + ((sizeof(int) * (size_t)N + 255) / 256) * 256);
+  MMR_CUDA(cudaMemcpyAsync(d_perm, h_perm, sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
+  for (int64_t j = 0; j < nrhs; ++j) {
+    double* b = d_B + j * N64;
+    rc = mmr_lu_tri_solves(ctx, N, d_LU, ld, b);
+    if (rc) return rc;
+    MMR_CUDA(cudaMemcpyAsync(d_tmp, b, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+    lu_gather_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, ctx->stream>>>(d_tmp, d_perm, N, b);
+    MMR_CHECK_LAUNCH(ctx);
+  }
+  return 0;
+}
