@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the demagnetization hot path (BASELINE.json metric: apply_demag seconds and
+demag_tensor entries/s at 8k / 64k cells, 1/2/4/8 B200 next to the CPU path).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--solver lu|gmres]
+
+One "step" = one full pass of the hot path on the workload: assemble Q = I - chi*T (9 n^2 FP64
+entries) and solve Q x = J0 + chi*H_ext.  Headline unit: T-entries per second of the whole step
+(9 n^2 / step seconds); ms_per_step is the apply_demag device time itself.
+
+  value  : inputs (cell geometry, chi, rhs) already resident in HBM, CUDA events around K steps.
+  e2e    : the same step through the public array-level API `apply_demag_arrays` with HOST numpy
+           buffers -- H2D of the geometry and D2H of the solution inside the timed region.
+  roofline     : dominant kernel (LU trailing DMMA update, or the matvec for --solver gmres),
+                 timed live with CUDA events inside the library (mmr_ctx_profile).
+  cpu_baseline : the numpy oracle (restated reference path) on a bounded sample, rank 0, N=1.
+
+--impl reference times the reference's own CPU algorithm (oracle port: magpylib is not
+installable here) on the host cores for the same metric.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOP_PER_PAIR_ALIGNED = 2162.0  # SURVEY 8d convention (sqrt=20, log=50, atan2=65, add/mul=1)
+FLOP_PER_PAIR_ROTATED = 2288.0
+
+
+# ----------------------------------------------------------------------------------------
+# workloads (synthetic geometry of the BASELINE configs; arrays only, no objects)
+# ----------------------------------------------------------------------------------------
+def mesh_arrays(dimension, nnn, position=(0, 0, 0), quat=(0, 0, 0, 1)):
+    from scipy.spatial.transform import Rotation as R
+
+    dim0 = np.asarray(dimension, dtype=float)
+    nnn = np.asarray(nnn, dtype=int)
+    axes = [np.linspace(d / 2 * (1 / n - 1), d / 2 * (1 - 1 / n), n) for d, n in zip(dim0, nnn, strict=True)]
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    rot = R.from_quat(quat)
+    n = len(grid)
+    return rot.apply(grid) + np.asarray(position, float), np.tile(np.asarray(quat, float), (n, 1)), np.tile(dim0 / nnn, (n, 1))
+
+
+def make_workload(name):
+    """Returns dict(pos, quat, dim, pol, chi, H_ext, desc).  pol in the LOCAL frame."""
+    from scipy.spatial.transform import Rotation as R
+
+    if name.startswith("two_magnets_"):
+        # BASELINE configs[1]: hard magnet (chi 0.5) + soft-iron cube (chi 1000) rotated 45 deg
+        # about y, docs/examples/soft_magnets.md:47-57; each meshed a x a x a/2
+        n = int(name.split("_")[-1])
+        a = round((n / 2 * 2) ** (1 / 3))
+        nnn = (a, a, a // 2)
+        p1, q1, d1 = mesh_arrays((1e-3, 1e-3, 2e-3), nnn, position=(0, 0, 0.5e-3))
+        p2, q2, d2 = mesh_arrays((1e-3, 1e-3, 1e-3), nnn, position=(1.5e-3, 0, 0),
+                                 quat=R.from_euler("y", 45, degrees=True).as_quat())
+        m = len(p1)
+        return dict(
+            pos=np.vstack([p1, p2]), quat=np.vstack([q1, q2]), dim=np.vstack([d1, d2]),
+            pol=np.vstack([np.tile((0, 0, 1.0), (m, 1)), np.zeros((m, 3))]),
+            chi=np.vstack([np.full((m, 3), 0.5), np.full((m, 3), 1000.0)]), H_ext=np.zeros((2 * m, 3)),
+            desc=f"hard magnet chi=0.5 + soft-iron cube chi=1000 rotated 45deg, 2 x {nnn[0]}x{nnn[1]}x{nnn[2]} = {2 * m} cells",
+        )
+    if name.startswith("soft_cube_"):
+        # north-star target / configs[3]: single soft-iron cube, chi=1000, H_ext=(0,0,1)
+        n = int(name.split("_")[-1])
+        a = round(n ** (1 / 3))
+        p, q, d = mesh_arrays((1e-3,) * 3, (a, a, a))
+        m = len(p)
+        return dict(pos=p, quat=q, dim=d, pol=np.zeros((m, 3)), chi=np.full((m, 3), 1000.0),
+                    H_ext=np.tile((0, 0, 1.0), (m, 1)),
+                    desc=f"soft-iron cube chi=1000, H_ext=(0,0,1), {a}x{a}x{a} = {m} cells")
+    msg = f"unknown workload {name}"
+    raise ValueError(msg)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(",") for r in pathlib.Path(self.tmp.name).read_text().strip().splitlines() if r.count(",") >= 6]
+        os.unlink(self.tmp.name)
+        if not rows:
+            return out
+        sm = [float(r[0]) for r in rows]
+        pw = [float(r[2]) for r in rows]
+        loaded = [s for s, p in zip(sm, pw, strict=True) if p > 0.5 * max(pw)] or sm
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any("Active" in r[3 + k] and "Not" not in r[3 + k] for r in rows)]
+        out.update(sm_mhz=statistics.median(loaded), sm_max_mhz=float(rows[0][1]), reasons=reasons, samples=len(rows),
+                   power_w_max=max(pw))
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port on host cores)
+# ----------------------------------------------------------------------------------------
+def cpu_sample_workload(name, n_sample):
+    kind = name.rsplit("_", 1)[0]
+    return make_workload(f"{kind}_{n_sample}")
+
+
+def time_oracle_step(w, split):
+    """One full reference step on the CPU: 3 getH passes, dense S@T, np.linalg.solve."""
+    from oracle import demag_ref as oref
+
+    t0 = time.perf_counter()
+    oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], H_ext=w["H_ext"], split=split)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(name, budget_s=20.0):
+    """Oracle timed on a bounded sample of the same workload geometry."""
+    n_sample = 2000 if "two_magnets" in name else 1728
+    w = cpu_sample_workload(name, n_sample)
+    n = len(w["pos"])
+    t = time_oracle_step(w, split=4)
+    reps = 1
+    while t * (reps + 1) < budget_s / 2 and reps < 3:
+        t = min(t, time_oracle_step(w, split=4))
+        reps += 1
+    return {
+        "value": 9.0 * n * n / t, "unit": "T-entries/s", "cores": os.cpu_count(), "kind": "port",
+        "sample": f"{w['desc']} (reduced from the full workload), full reference step "
+                  f"(3 getH passes + dense S@T + LAPACK dgesv) in {t:.2f} s; numpy ufuncs run on 1 thread, BLAS/LAPACK on all cores",
+        "seconds": t, "n_cells": n,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload or default_workload(args.gpus)
+    total = args.steps + args.warmup
+    n_sample = 2000 if total <= 6 else 1000
+    if "soft_cube" in name:
+        n_sample = 1728 if total <= 6 else 1000
+    w = cpu_sample_workload(name, n_sample)
+    n = len(w["pos"])
+    for _ in range(args.warmup):
+        time_oracle_step(w, split=4)
+    times = [time_oracle_step(w, split=4) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    value = 9.0 * n * n / t
+    line = {
+        "impl": "reference", "metric": "apply_demag_T_entries_per_s", "value": value, "unit": "T-entries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "sample": w["desc"], "solver": "numpy.linalg.solve (dgesv)",
+                   "note": "restated oracle of the reference CPU path (magpylib not installable); bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": "T-entries/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{w['desc']}; {t:.2f} s per full reference step"},
+        "e2e": {"value": value, "unit": "T-entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def default_workload(ngpus):
+    return "two_magnets_8000"
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "fp64_dmma_tflops": 37.1,
+             "fp64_fma_tflops": 33.9, "fp64_src": "profiles/fp64_peaks_r1.json (tools/fp64_peaks.cu, measured on this pool)"}
+    mp = ROOT / "MEASURED_PEAKS.json"
+    if mp.exists():
+        d = json.loads(mp.read_text())
+        peaks["hbm_gbs"], peaks["hbm_src"] = d.get("hbm_gbs", peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    fp = ROOT / "profiles" / "fp64_peaks_r1.json"
+    if fp.exists():
+        d = json.loads(fp.read_text())
+        peaks["fp64_dmma_tflops"], peaks["fp64_fma_tflops"] = d["fp64_dmma_tflops"], d["fp64_fma_tflops"]
+    return peaks
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from magpylib_material_response_b200 import _native
+    from magpylib_material_response_b200.demag import _padded_ld, apply_demag_arrays
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the demag path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    name = args.workload or default_workload(world)
+    w = make_workload(name)
+    n = len(w["pos"])
+    N = 3 * n
+    rotated = bool(np.any(w["quat"][:, :3] != 0))
+    ctx = _native.default_context(local_rank)
+    if world > 1:
+        ctx.comm_init_from_torch()
+    peaks = load_peaks()
+
+    from scipy.spatial.transform import Rotation as R
+
+    rot = R.from_quat(w["quat"])
+    rhs_host = (rot.apply(w["pol"]) + w["chi"] * w["H_ext"]).reshape(N)
+    d_pos, d_quat, d_dim = ctx.to_device(w["pos"]), ctx.to_device(w["quat"]), ctx.to_device(w["dim"])
+    d_chi, d_rhs = ctx.to_device(w["chi"].reshape(N)), ctx.to_device(rhs_host)
+    ld = _padded_ld(N)
+
+    # row-block ownership (block-cyclic over cells); single GPU owns everything
+    tgt_block = 64 if world > 1 else n
+    nblk = -(-n // tgt_block)
+    my_blocks = list(range(rank, nblk, world))
+    n_local = sum(min(tgt_block, n - b * tgt_block) for b in my_blocks)
+    Q = ctx.empty(3 * n_local, ld)
+    ipiv = ctx.empty(N, dtype=torch.int32)
+    d_x = ctx.empty(N)
+    solver = args.solver
+    if world > 1 and solver == "lu" and not args.dist_lu:
+        solver = "gmres"  # distributed LU is selected explicitly; default multi-GPU solver is GMRES
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device) if 8.0 * N * ld * 3 < 512e6 else None
+
+    def step():
+        if flush is not None:
+            flush.zero_()  # inputs smaller than L2 would otherwise stay cached
+        ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, n_tgt_local=n_local, tgt_block=tgt_block,
+                     tgt_nparts=world, tgt_part=rank)
+        d_x.copy_(d_rhs)
+        if world == 1:
+            if solver == "lu":
+                info = ctx.lu_factor(Q, ld, ipiv)
+                assert info == 0
+                ctx.lu_solve(Q, ld, ipiv, d_x)
+                return None
+            d_x.zero_()
+            return ctx.gmres(Q, ld, d_rhs, d_x, tol=args.tol, restart=300, maxit=5000)
+        if solver == "lu":
+            info = ctx.lu_solve_dist(N, 3 * n_local, tgt_block, Q, ld, d_x)
+            assert info == 0
+            return None
+        d_x.zero_()
+        return ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_rhs, d_x, tol=args.tol, restart=300, maxit=5000)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gm = None
+    for _ in range(args.steps):
+        gm = step()
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([t_dev], dtype=torch.float64, device=ctx.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+    t_step = t_dev / args.steps
+
+    # residual of the last solution (not timed): ||Q x - b|| / ||b|| on a fresh Q
+    ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, n_tgt_local=n_local, tgt_block=tgt_block,
+                 tgt_nparts=world, tgt_part=rank)
+    relres = None
+    if world == 1:
+        y = ctx.empty(N)
+        ctx.matvec(Q, ld, d_x, y)
+        relres = float(torch.linalg.norm(y - d_rhs) / torch.linalg.norm(d_rhs))
+
+    # e2e through the public array API with host buffers (single GPU only; rank 0)
+    e2e = None
+    if world == 1:
+        del Q
+        torch.cuda.empty_cache()
+        kw = dict(solver=solver, tol=args.tol)
+        apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw)
+        torch.cuda.synchronize()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            xs = apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw)
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / reps
+        h2d = 8 * (n * 3 + n * 4 + n * 3 + N + N)  # pos, quat, dim, chi, rhs
+        d2h = 8 * N
+        e2e = {"value": 9.0 * n * n / t_e2e, "unit": "T-entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "seconds_per_step": t_e2e, "api": "magpylib_material_response_b200.demag.apply_demag_arrays (host numpy in/out)"}
+        del xs
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    asm_ms, asm_pairs, asm_cnt = prof["assemble"]
+    gemm_ms, gemm_flops, gemm_cnt = prof["gemm"]
+    mv_ms, mv_bytes, mv_cnt = prof["matvec"]
+    fpp = FLOP_PER_PAIR_ROTATED if rotated else FLOP_PER_PAIR_ALIGNED
+    roof_asm = {"bound": "fp64", "achieved": asm_pairs * fpp / (asm_ms * 1e-3) / 1e12 if asm_ms else None,
+                "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s (flop-equivalents, SURVEY 8d convention)",
+                "traffic": None, "kernel": "assemble_cell_major_kernel", "ms_per_launch": asm_ms / max(1, asm_cnt),
+                "entries_per_s": 9.0 * asm_pairs / (asm_ms * 1e-3) if asm_ms else None, "peak_src": peaks["fp64_src"]}
+    if roof_asm["achieved"]:
+        roof_asm["frac"] = roof_asm["achieved"] / roof_asm["peak"]
+    if solver == "lu" and gemm_ms:
+        ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["fp64_dmma_tflops"], "traffic": None, "kernel": "dgemm_nn_kernel (LU trailing update, DMMA.8x8x4)",
+                    "launches": gemm_cnt, "ms_per_launch": gemm_ms / gemm_cnt,
+                    "peak_src": "FP64 DMMA peak " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry"}
+    elif mv_ms:
+        ach = mv_bytes / (mv_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "kernel": "matvec_rows_kernel (GMRES)", "launches": mv_cnt, "ms_per_launch": mv_ms / mv_cnt,
+                    "peak_src": peaks["hbm_src"]}
+    else:
+        roofline = roof_asm
+
+    stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps} for k, v in prof.items() if v[2]}
+    lu_flops = (2.0 / 3.0) * N**3
+    lu_ms = sum(prof[k][0] for k in ("gemm", "panel", "trsm", "laswp", "panel_gemm")) / args.steps
+    line = {
+        "metric": "apply_demag_T_entries_per_s", "value": 9.0 * n * n / t_step, "unit": "T-entries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "desc": w["desc"], "n_cells": n, "matrix_order": N, "solver": solver,
+                   "row_block_cells": tgt_block, "l2": "inputs larger than L2 (Q is %.1f GB)" % (8.0 * N * ld / 1e9)
+                   if flush is None else "256 MB flush buffer written before every step"},
+        "apply_demag_s": t_step,
+        "assembly_entries_per_s": roof_asm["entries_per_s"],
+        "lu_factor_tflops": lu_flops / (lu_ms * 1e-3) / 1e12 if (solver == "lu" and lu_ms) else None,
+        "gmres": {"iters": gm[0], "relres": gm[1]} if gm else None,
+        "relres_check": relres,
+        "stages": stages,
+        "roofline": roofline,
+        "roofline_assembly": roof_asm,
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(name)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="two_magnets_<n> | soft_cube_<n>")
+    ap.add_argument("--solver", default="lu", choices=["lu", "gmres"])
+    ap.add_argument("--dist-lu", action="store_true", help="use the distributed LU for --gpus > 1")
+    ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

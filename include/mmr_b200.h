@@ -67,6 +67,22 @@ int mmr_ctx_sync(mmr_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t mmr_ctx_launch_count(mmr_ctx* ctx);
 
+/* Optional per-kernel-class timing with CUDA events on the context's stream (bench.py's live
+ * roofline).  set_profiling(on) clears the records; profile() synchronizes the stream and
+ * returns the summed duration (ms), summed algorithmic units and launch count of one class. */
+#define MMR_PROF_ASSEMBLE 0   /* units: cell pairs evaluated                    */
+#define MMR_PROF_GEMM 1       /* units: flops of the LU trailing DMMA updates   */
+#define MMR_PROF_PANEL 2      /* units: panel columns factored (strip kernels)  */
+#define MMR_PROF_TRSM 3       /* units: flops                                   */
+#define MMR_PROF_LASWP 4      /* units: bytes moved                             */
+#define MMR_PROF_MATVEC 5     /* units: matrix bytes streamed                   */
+#define MMR_PROF_PANEL_GEMM 6 /* units: flops of the in-panel rank-W updates    */
+#define MMR_PROF_TRISOLVE 7   /* units: matrix bytes streamed                   */
+#define MMR_PROF_NKINDS 8
+int mmr_ctx_set_profiling(mmr_ctx* ctx, int on);
+int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
+                    int64_t* launches_out);
+
 /* ---- kernel 1: demag tensor assembly (demag.py:124-224 + :451-452 + :466) ------------- */
 /*
  * Evaluates the analytic cuboid H-field block of every source cell i in [src_begin,src_end)

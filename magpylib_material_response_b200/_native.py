@@ -43,6 +43,12 @@ _SIGNATURES = {
     "mmr_ctx_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mmr_ctx_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "mmr_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mmr_ctx_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "mmr_ctx_profile": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+         ctypes.POINTER(ctypes.c_int64)],
+    ),
     "mmr_assemble": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]
@@ -200,7 +206,7 @@ class Context:
     def to_device(self, arr):
         import numpy as np
 
-        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        t = self.torch.from_numpy(np.array(arr, dtype=np.float64, order="C", copy=True))
         return t.to(self.device, non_blocking=False)
 
     def empty(self, *shape, dtype=None):
@@ -212,6 +218,21 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.mmr_ctx_launch_count(self.handle))
+
+    PROF_KINDS = ("assemble", "gemm", "panel", "trsm", "laswp", "matvec", "panel_gemm", "trisolve")
+
+    def set_profiling(self, on=True):
+        _check(self.lib, self.lib.mmr_ctx_set_profiling(self.handle, int(bool(on))))
+
+    def profile(self):
+        """{kind: (ms, units, launches)} for every kernel class recorded since set_profiling."""
+        out = {}
+        for k, name in enumerate(self.PROF_KINDS):
+            ms, units, cnt = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+            _check(self.lib, self.lib.mmr_ctx_profile(self.handle, k, ctypes.byref(ms), ctypes.byref(units),
+                                                      ctypes.byref(cnt)))
+            out[name] = (ms.value, units.value, cnt.value)
+        return out
 
     # ---- kernel 1 --------------------------------------------------------------------
     def assemble(self, pos, quat, dim, out, ld, *, chi=None, max_dist=0.0, layout=LAYOUT_CELL_MAJOR,

@@ -282,8 +282,10 @@ extern "C" int mmr_assemble(mmr_ctx* ctx, int64_t n, const double* d_pos, const 
   p.tgt_nparts = tgt_nparts; p.tgt_part = tgt_part;
   p.chi = d_chi; p.max_dist = max_dist; p.out = d_out; p.ld = ld;
 
+  const double npairs = (double)(src_end - src_begin) * (double)n_tgt_local;
   if (layout == MMR_LAYOUT_CELL_MAJOR) {
     MMR_ARG(ld >= 3 * n, "ld must be >= 3*n for the cell-major layout");
+    const int pidx = mmr_prof_begin(ctx, MMR_PROF_ASSEMBLE, ctx->stream);
     dim3 grid((unsigned)ceil_div64(src_end - src_begin, SRC_TILE),
               (unsigned)ceil_div64(n_tgt_local, TGT_TILE));
     if (rotated) {
@@ -293,6 +295,7 @@ extern "C" int mmr_assemble(mmr_ctx* ctx, int64_t n, const double* d_pos, const 
       if (d_chi) launch_cell_major<false, true>(p, grid, ctx->stream);
       else launch_cell_major<false, false>(p, grid, ctx->stream);
     }
+    mmr_prof_end(ctx, pidx, npairs, ctx->stream);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }

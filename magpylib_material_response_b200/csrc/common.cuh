@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/mmr_b200.h"
 
@@ -31,6 +32,15 @@ struct mmr_ctx {
   void* nccl_comm = nullptr;
   int nranks = 1;
   int rank = 0;
+  // optional profiling records (mmr_ctx_set_profiling)
+  bool profiling = false;
+  struct ProfRec {
+    int kind;
+    cudaEvent_t e0, e1;
+    double units;
+  };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
   // side stream + events for look-ahead in the LU
   cudaStream_t side = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -75,5 +85,9 @@ struct DeviceGuard {
 int mmr_ws_reserve(mmr_ctx* ctx, size_t bytes);    // ctx->ws
 int mmr_ws2_reserve(mmr_ctx* ctx, size_t bytes);   // ctx->ws2
 int mmr_hpin_reserve(mmr_ctx* ctx, size_t bytes);  // ctx->hpin
+
+// profiling scope: records an event pair around the launches enqueued in between
+int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s);
+void mmr_prof_end(mmr_ctx* ctx, int idx, double units, cudaStream_t s);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -43,6 +43,70 @@ int mmr_hpin_reserve(mmr_ctx* ctx, size_t bytes) {
   return reserve(&ctx->hpin, &ctx->hpin_bytes, bytes, true);
 }
 
+static cudaEvent_t prof_event(mmr_ctx* ctx) {
+  if (!ctx->prof_pool.empty()) {
+    cudaEvent_t e = ctx->prof_pool.back();
+    ctx->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s) {
+  if (!ctx->profiling) return -1;
+  mmr_ctx::ProfRec r;
+  r.kind = kind;
+  r.e0 = prof_event(ctx);
+  r.e1 = prof_event(ctx);
+  r.units = 0.0;
+  cudaEventRecord(r.e0, s);
+  ctx->prof.push_back(r);
+  return (int)ctx->prof.size() - 1;
+}
+
+void mmr_prof_end(mmr_ctx* ctx, int idx, double units, cudaStream_t s) {
+  if (idx < 0) return;
+  ctx->prof[idx].units = units;
+  cudaEventRecord(ctx->prof[idx].e1, s);
+}
+
+extern "C" int mmr_ctx_set_profiling(mmr_ctx* ctx, int on) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof) {
+    ctx->prof_pool.push_back(r.e0);
+    ctx->prof_pool.push_back(r.e1);
+  }
+  ctx->prof.clear();
+  ctx->profiling = on != 0;
+  return 0;
+}
+
+extern "C" int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
+                               int64_t* launches_out) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(kind >= 0 && kind < MMR_PROF_NKINDS, "unknown profile kind");
+  DeviceGuard g(ctx->device);
+  MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+  double ms = 0.0, units = 0.0;
+  int64_t cnt = 0;
+  for (auto& r : ctx->prof) {
+    if (r.kind != kind) continue;
+    float t = 0.f;
+    MMR_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    units += r.units;
+    ++cnt;
+  }
+  if (ms_out) *ms_out = ms;
+  if (units_out) *units_out = units;
+  if (launches_out) *launches_out = cnt;
+  return 0;
+}
+
 extern "C" int mmr_abi_version(void) { return MMR_ABI_VERSION; }
 extern "C" const char* mmr_last_error(void) { return g_err; }
 
@@ -80,6 +144,11 @@ extern "C" int mmr_ctx_destroy(mmr_ctx* ctx) {
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   mmr_comm_destroy(ctx);
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);

@@ -140,10 +140,12 @@ int launch_matvec(mmr_ctx* ctx, int64_t nrows, int64_t ncols, const double* Q, i
                   double* y) {
   if (nrows == 0) return 0;
   const bool vec2 = (((uintptr_t)Q | (uintptr_t)x) % 16 == 0) && (ld % 2 == 0);
+  const int pidx = mmr_prof_begin(ctx, MMR_PROF_MATVEC, ctx->stream);
   if (vec2)
     matvec_rows_kernel<true><<<(unsigned)nrows, MV_THREADS, 0, ctx->stream>>>(nrows, ncols, Q, ld, x, y);
   else
     matvec_rows_kernel<false><<<(unsigned)nrows, MV_THREADS, 0, ctx->stream>>>(nrows, ncols, Q, ld, x, y);
+  mmr_prof_end(ctx, pidx, 8.0 * nrows * (double)ncols, ctx->stream);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }

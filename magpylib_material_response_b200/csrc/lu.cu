@@ -424,8 +424,10 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
     }
     int w_arg = w, N_arg = N, c0_arg = c0;
     void* args[] = {&A, &ld, &N_arg, &c0_arg, &w_arg, &rows_per, &d_ipiv, &cand, &candrow, &diagrow, &d_info};
+    const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, ctx->stream);
     MMR_CUDA(cudaLaunchCooperativeKernel((void*)lu_strip_kernel, dim3(G), dim3(STRIP_THREADS), args, smem,
                                          ctx->stream));
+    mmr_prof_end(ctx, pidx, (double)w, ctx->stream);
     ctx->launches++;
     const int ncol_other = nb - w;
     if (ncol_other > 0) {
@@ -435,10 +437,12 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
     const int nright = kb + nb - (c0 + w);
     const int mbelow = N - (c0 + w);
     if (nright > 0 && mbelow > 0) {
+      const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, ctx->stream);
       int rc = mmr_dgemm_launch(ctx, ctx->stream, mbelow, nright, w, -1.0,
                                 A + (int64_t)c0 * ld + (c0 + w), ld,
                                 A + (int64_t)(c0 + w) * ld + c0, ld, 1.0,
                                 A + (int64_t)(c0 + w) * ld + (c0 + w), ld);
+      mmr_prof_end(ctx, pg, 2.0 * mbelow * nright * w, ctx->stream);
       if (rc) return rc;
     }
   }
@@ -493,20 +497,28 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
     rc = mmr_lu_panel(ctx, A, ld, N, kb, nb, d_ipiv, d_info, scratch);
     if (rc) return rc;
     // swaps on the columns left and right of the panel
+    const int ntrail = N - (kb + nb);
+    int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, ctx->stream);
     rc = mmr_lu_laswp(ctx, A, ld, kb, kb + nb, 0, kb, d_ipiv);
     if (rc) return rc;
-    const int ntrail = N - (kb + nb);
     if (ntrail > 0) {
       rc = mmr_lu_laswp(ctx, A, ld, kb, kb + nb, kb + nb, N, d_ipiv);
       if (rc) return rc;
+    }
+    mmr_prof_end(ctx, ps, 32.0 * nb * (double)(N - nb), ctx->stream);
+    if (ntrail > 0) {
       // U12 = L11^-1 A12
+      ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, ctx->stream);
       rc = mmr_lu_trsm(ctx, A + (int64_t)kb * ld + kb, ld, nb, A + (int64_t)(kb + nb) * ld + kb, ld, ntrail);
       if (rc) return rc;
+      mmr_prof_end(ctx, ps, (double)nb * nb * ntrail, ctx->stream);
       // A22 -= L21 U12
+      ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, ctx->stream);
       rc = mmr_dgemm_launch(ctx, ctx->stream, ntrail, ntrail, nb, -1.0, A + (int64_t)kb * ld + (kb + nb), ld,
                             A + (int64_t)(kb + nb) * ld + kb, ld, 1.0,
                             A + (int64_t)(kb + nb) * ld + (kb + nb), ld);
       if (rc) return rc;
+      mmr_prof_end(ctx, ps, 2.0 * ntrail * (double)ntrail * nb, ctx->stream);
     }
   }
   MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -585,8 +597,10 @@ extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64
   MMR_CUDA(cudaMemcpyAsync(d_perm, h_perm, sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
   for (int64_t j = 0; j < nrhs; ++j) {
     double* b = d_B + j * N64;
+    const int pt = mmr_prof_begin(ctx, MMR_PROF_TRISOLVE, ctx->stream);
     rc = mmr_lu_tri_solves(ctx, N, d_LU, ld, b);
     if (rc) return rc;
+    mmr_prof_end(ctx, pt, 8.0 * N * (double)N, ctx->stream);
     MMR_CUDA(cudaMemcpyAsync(d_tmp, b, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
     lu_gather_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, ctx->stream>>>(d_tmp, d_perm, N, b);
     MMR_CHECK_LAUNCH(ctx);

@@ -24,6 +24,7 @@ from .utils import timelog
 
 __all__ = [
     "apply_demag",
+    "apply_demag_arrays",
     "demag_tensor",
     "filter_distance",
     "get_H_ext",
@@ -308,6 +309,78 @@ def _rotate_rows(src_list, vecs, inverse=False):
     return rot.apply(vecs, inverse=inverse)
 
 
+def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching=False, max_dist=0,
+                       split=1, solver="lu", tol=1e-12, device=None, min_log_time=None):
+    """Host arrays in, host array out: assemble Q = I - chi*N on the device, solve
+    Q x = J0 + chi*H_ext (demag.py:444-470).  All (n,3) arrays, GLOBAL frame.  Returns (x, info)."""
+    ctx = _native.default_context(device)
+    torch = ctx.torch
+    n = len(pos)
+    N = 3 * n
+    info = {}
+    rhs = (np.asarray(pol_global, dtype=float) + np.asarray(chi, dtype=float) * np.asarray(H_ext, dtype=float)).reshape(N)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record(ctx.stream)
+    with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):
+        Q, ld = _assemble_device(
+            ctx, pos, quat, dim, chi_cell_major=np.asarray(chi, dtype=float).reshape(N),
+            pairs_matching=pairs_matching, max_dist=max_dist, split=split,
+        )
+    ev[1].record(ctx.stream)
+    with timelog("Solving of linear system", min_log_time=min_log_time):
+        d_x = ctx.to_device(rhs)
+        if solver == "lu":
+            ipiv = ctx.empty(N, dtype=torch.int32)
+            lu_info = ctx.lu_factor(Q, ld, ipiv)
+            if lu_info != 0:
+                msg = f"Singular matrix (zero pivot at elimination step {lu_info})"
+                raise np.linalg.LinAlgError(msg)
+            ev[2].record(ctx.stream)
+            ctx.lu_solve(Q, ld, ipiv, d_x)
+        else:
+            d_b = d_x
+            d_x = d_b.clone()
+            ev[2].record(ctx.stream)
+            iters, relres = ctx.gmres(Q, ld, d_b, d_x, tol=tol, restart=min(300, N), maxit=max(1000, 2 * N))
+            info["gmres_iters"], info["gmres_relres"] = iters, relres
+        ev[3].record(ctx.stream)
+        x = d_x.cpu().numpy().reshape(n, 3)
+    info["assemble_ms"] = ev[0].elapsed_time(ev[1])
+    info["factor_ms"] = ev[1].elapsed_time(ev[2])
+    info["solve_ms"] = ev[2].elapsed_time(ev[3])
+    return x, info
+
+
+def apply_demag_arrays(pos, quat, dim, pol, chi, H_ext=None, *, pairs_matching=False, max_dist=0, split=1,
+                       solver="lu", tol=1e-12, device=None, return_info=False):
+    """Array-level form of ``apply_demag`` (structure-of-arrays in host memory, no objects):
+    pos (n,3), quat (n,4) scalar-last, dim (n,3), pol (n,3) LOCAL-frame polarizations, chi scalar /
+    (3,) / (n,) / (n,3), H_ext (n,3) or (3,).  Returns the solved LOCAL-frame polarizations (n,3).
+    Same mathematics as demag.py:420-476; this is the call the end-to-end benchmark times."""
+    from scipy.spatial.transform import Rotation as R
+
+    pos = np.ascontiguousarray(pos, dtype=float).reshape(-1, 3)
+    n = len(pos)
+    quat = np.ascontiguousarray(np.broadcast_to(np.asarray(quat, dtype=float), (n, 4)))
+    dim = np.ascontiguousarray(np.broadcast_to(np.asarray(dim, dtype=float), (n, 3)))
+    pol = np.broadcast_to(np.asarray(pol, dtype=float), (n, 3))
+    chi_a = np.asarray(chi, dtype=float)
+    if chi_a.ndim == 1 and chi_a.shape == (n,) and n != 3:
+        chi_a = chi_a[:, None]
+    chi_a = np.broadcast_to(chi_a, (n, 3))
+    H = np.zeros((n, 3)) if H_ext is None else np.broadcast_to(np.asarray(H_ext, dtype=float), (n, 3))
+    if pairs_matching and split != 1:
+        msg = "Pairs matching does not support splitting"
+        raise ValueError(msg)
+    if n == 0:
+        return (np.zeros((0, 3)), {}) if return_info else np.zeros((0, 3))
+    rot = R.from_quat(quat)
+    x, info = solve_cells_global(pos, quat, dim, rot.apply(pol), chi_a, H, pairs_matching=pairs_matching,
+                                 max_dist=max_dist, split=split, solver=solver, tol=tol, device=device)
+    out = rot.apply(x, inverse=True)
+    return (out, info) if return_info else out
+
+
 def apply_demag(
     collection,
     susceptibility=None,
@@ -401,44 +474,12 @@ def apply_demag(
             return (collection if not inplace else None) if not return_info else (collection, info)
         _check_native_cells(magnets_list)
 
-        ctx = _native.default_context(device)
-        torch = ctx.torch
         pos, quat, dim = _cell_geometry(magnets_list)
-        N = 3 * n
-
-        # rhs = J0 + chi * H_ext (demag.py:470), cell-major
-        rhs = (pol_global + chi * H_ext).reshape(N)
-
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record(ctx.stream)
-        with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):
-            Q, ld = _assemble_device(
-                ctx, pos, quat, dim, chi_cell_major=chi.reshape(N),
-                pairs_matching=pairs_matching, max_dist=max_dist, split=split,
-            )
-        ev[1].record(ctx.stream)
-        with timelog("Solving of linear system", min_log_time=min_log_time):
-            d_x = ctx.to_device(rhs)
-            if solver == "lu":
-                ipiv = ctx.empty(N, dtype=torch.int32)
-                lu_info = ctx.lu_factor(Q, ld, ipiv)
-                if lu_info != 0:
-                    msg = f"Singular matrix (zero pivot at elimination step {lu_info})"
-                    raise np.linalg.LinAlgError(msg)
-                ev[2].record(ctx.stream)
-                ctx.lu_solve(Q, ld, ipiv, d_x)
-            else:
-                d_b = d_x
-                d_x = d_b.clone()
-                ev[2].record(ctx.stream)
-                iters, relres = ctx.gmres(Q, ld, d_b, d_x, tol=tol, restart=min(300, N), maxit=max(1000, 2 * N))
-                info["gmres_iters"], info["gmres_relres"] = iters, relres
-            ev[3].record(ctx.stream)
-            pol_new = d_x.cpu().numpy().reshape(n, 3)  # global frame, cell-major
-        info["assemble_ms"] = ev[0].elapsed_time(ev[1])
-        info["factor_ms"] = ev[1].elapsed_time(ev[2])
-        info["solve_ms"] = ev[2].elapsed_time(ev[3])
-        del Q
+        pol_new, solve_info = solve_cells_global(
+            pos, quat, dim, pol_global, chi, H_ext, pairs_matching=pairs_matching, max_dist=max_dist,
+            split=split, solver=solver, tol=tol, device=device, min_log_time=min_log_time,
+        )
+        info.update(solve_info)
 
         # write back in each cell's local frame (demag.py:472-476); by magnet index (Appendix A Q7)
         pol_write = _rotate_rows(magnets_list, pol_new, inverse=True)

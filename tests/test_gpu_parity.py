@@ -1,0 +1,440 @@
+"""GPU parity tests (run with -m gpu on a B200).  Every check compares the CUDA path -- called
+through the C ABI (ctypes) -- with the CPU oracle on the same seeded inputs, with the committed
+goldens, or (at full BASELINE sizes) with size-independent properties.
+
+Tolerances (BASELINE.json north_star / SURVEY 7.2):
+  T entries : |dT| <= 1e-10 * |T_ref| + 2e-15   (the FP64 closed form itself carries ~1e-16
+              absolute error, so a pure rtol is not attainable for far pairs)
+  solutions : |dJ| <= 1e-8 * max|J|  (component-wise against the cell's largest component)
+"""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+import torch
+from scipy.spatial.transform import Rotation as R
+
+import magpylib_material_response_b200 as mmr
+from magpylib_material_response_b200 import Collection, Cuboid, _native, apply_demag, demag_tensor, mesh_Cuboid
+from magpylib_material_response_b200.demag import _assemble_device, _cell_geometry
+from oracle import cuboid_field as ocf
+from oracle import demag_ref as oref
+
+pytestmark = pytest.mark.gpu
+
+T_RTOL, T_ATOL = 1e-10, 2e-15
+J_RTOL = 1e-8
+
+
+def assert_T_close(got, ref):
+    err = np.abs(got - ref)
+    tol = T_RTOL * np.abs(ref) + T_ATOL
+    bad = err > tol
+    assert not bad.any(), f"{bad.sum()} entries off; worst abs err {err.max():.3e}"
+
+
+def random_cells(n, seed=0):
+    """SURVEY 8d random-geometry stress: rotations, unequal sizes, overlaps."""
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(-1e-3, 1e-3, (n, 3))
+    dim = rng.uniform(0.05e-3, 0.3e-3, (n, 3))
+    quat = R.random(n, rng).as_quat()
+    chi = rng.uniform(-0.5, 5, (n, 3))
+    pol = rng.normal(0, 1, (n, 3))
+    return pos, quat, dim, chi, pol
+
+
+def cell_major_to_reference(Nmat, n):
+    """device matrix [3j+l, 3i+k] -> reference Tmat [l*n+j, k*n+i] (demag.py:452)."""
+    return Nmat.reshape(n, 3, n, 3).transpose(1, 0, 3, 2).reshape(3 * n, 3 * n)
+
+
+def dev(ctx, a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(ctx.device)
+
+
+def assemble_numpy(ctx, pos, quat, dim, **kw):
+    out, ld = _assemble_device(ctx, pos, quat, dim, **kw)
+    ctx.sync()
+    return out[:, : 3 * len(pos)].cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------
+# kernel 1: assembly
+# ---------------------------------------------------------------------------------------
+def test_native_library_is_loaded_and_counts_launches(ctx):
+    assert _native.LIB_PATH.exists()
+    before = ctx.launch_count
+    pos, quat, dim = oref.mesh_cuboid_arrays((1, 1, 1), (2, 2, 2))
+    assemble_numpy(ctx, pos, quat, dim)
+    assert ctx.launch_count > before
+
+
+def test_assembly_matches_mpmath_known_answers(ctx, golden_dir):
+    data = json.loads((golden_dir / "cuboid_known_answers.json").read_text())
+    for case in data["cases"]:
+        dimv = np.array(case["dim"])
+        off = np.array(case["offset"])
+        ref = np.array([[float(v) for v in row] for row in case["block_l_k"]])
+        self_case = not off.any()
+        pos = np.zeros((1, 3)) if self_case else np.stack([np.zeros(3), off])
+        n = len(pos)
+        quat = np.tile((0.0, 0, 0, 1), (n, 1))
+        dim = np.tile(dimv, (n, 1))
+        Nmat = assemble_numpy(ctx, pos, quat, dim)
+        blk = Nmat[0:3, 0:3] if self_case else Nmat[3:6, 0:3]  # target 1, source 0
+        np.testing.assert_allclose(blk, ref, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("shape", [(6, 6, 6), (5, 3, 7), (1, 1, 1), (1, 1, 2), (33, 1, 1)])
+def test_assembly_aligned_cells_vs_oracle(ctx, shape):
+    pos, quat, dim = oref.mesh_cuboid_arrays((1e-3, 1.3e-3, 0.7e-3), shape)
+    n = len(pos)
+    ref = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim))
+    got = cell_major_to_reference(assemble_numpy(ctx, pos, quat, dim), n)
+    assert_T_close(got, ref)
+    # trace identity: every self block has trace -1
+    np.testing.assert_allclose(np.trace(got), -n, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 31, 257])
+def test_assembly_random_rotated_cells_vs_oracle(ctx, n):
+    pos, quat, dim, _, _ = random_cells(n, seed=n)
+    ref = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim))
+    got = cell_major_to_reference(assemble_numpy(ctx, pos, quat, dim), n)
+    assert_T_close(got, ref)
+
+
+def test_assembly_two_magnets_rotated_soft_iron_geometry(ctx):
+    """Config-2 geometry at reduced size: hard magnet + soft cube rotated 45 deg about y."""
+    p1, q1, d1 = oref.mesh_cuboid_arrays((1e-3, 1e-3, 2e-3), (4, 4, 2), position=(0, 0, 0.5e-3))
+    p2, q2, d2 = oref.mesh_cuboid_arrays(
+        (1e-3, 1e-3, 1e-3), (4, 4, 2), position=(1.5e-3, 0, 0), quat=R.from_euler("y", 45, degrees=True).as_quat()
+    )
+    pos, quat, dim = np.vstack([p1, p2]), np.vstack([q1, q2]), np.vstack([d1, d2])
+    n = len(pos)
+    ref = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim))
+    got = cell_major_to_reference(assemble_numpy(ctx, pos, quat, dim), n)
+    assert_T_close(got, ref)
+
+
+def test_assembly_touching_cells_of_different_size_hit_surface_and_edge_cases(ctx):
+    """A small cell whose centre lies exactly on a face / edge / corner-edge extension of a big
+    one (SURVEY 7.2 'edge/surface special cases')."""
+    pos = np.array([[0, 0, 0], [0.5, 0, 0], [0.5, 0.5, 0], [0.5, 0.5, 0.5], [1.0, 0.5, 0.25], [0.5, 0.2, 0.1]])
+    dim = np.array([[1, 1, 1], [0.2, 0.2, 0.2], [0.2, 0.2, 0.2], [0.2, 0.2, 0.2], [0.2, 0.2, 0.2], [0.1, 0.3, 0.2]])
+    quat = np.tile((0.0, 0, 0, 1), (len(pos), 1))
+    n = len(pos)
+    ref = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim))
+    got = cell_major_to_reference(assemble_numpy(ctx, pos, quat, dim), n)
+    assert np.isfinite(got).all()
+    assert_T_close(got, ref)
+
+
+def test_public_demag_tensor_layout_units_split_and_no_mutation(ctx):
+    c = Cuboid(dimension=(1e-3, 2e-3, 1e-3), polarization=(0.1, 0.2, 0.3), orientation=R.from_rotvec((0.2, -0.1, 0.4)))
+    c.susceptibility = 1.0
+    mesh = mesh_Cuboid(c, (3, 4, 2))
+    srcs = mesh.sources_all
+    pos, quat, dim = _cell_geometry(srcs)
+    ref = oref.demag_tensor_ref(pos, quat, dim)
+    got = demag_tensor(srcs)
+    assert got.shape == (3, 24, 24, 3)
+    assert_T_close(got * ocf.MU0, ref * ocf.MU0)
+    got_split = demag_tensor(srcs, split=5)
+    np.testing.assert_array_equal(got_split, got)
+    # the reference mutates polarizations while assembling (demag.py:200-201); we do not
+    assert all(np.array_equal(s.polarization, (0.1, 0.2, 0.3)) for s in srcs)
+
+
+def test_fused_system_matrix_equals_I_minus_S_T(ctx):
+    pos, quat, dim, chi, _ = random_cells(97, seed=5)
+    n = len(pos)
+    Nmat = assemble_numpy(ctx, pos, quat, dim)
+    Q = assemble_numpy(ctx, pos, quat, dim, chi_cell_major=chi.reshape(-1))
+    expect = np.eye(3 * n) - chi.reshape(-1)[:, None] * Nmat
+    np.testing.assert_array_equal(Q, expect)  # the same single FP64 product (Appendix A Q8)
+    # and against the reference's dense S@T build
+    T = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim))
+    S = np.diag(oref.susceptibility_vector(chi, n))
+    Qref = np.eye(3 * n) - S @ T
+    assert_T_close(cell_major_to_reference(Q, n), Qref)
+
+
+@pytest.mark.parametrize("max_dist", [1.5, 2.0, 3.7, -1.0])
+def test_max_dist_masks_exactly_the_reference_pairs(ctx, max_dist):
+    pos, quat, dim = oref.mesh_cuboid_arrays((1e-3, 2e-3, 1e-3), (4, 5, 3))
+    n = len(pos)
+    ref = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim, max_dist=max_dist))
+    got = cell_major_to_reference(assemble_numpy(ctx, pos, quat, dim, max_dist=max_dist), n)
+    assert np.array_equal(got == 0, ref == 0)
+    assert_T_close(got, ref)
+
+
+def test_block_cyclic_target_sets_tile_the_full_matrix(ctx):
+    """Row-block sharding used by the multi-GPU path: the union of all parts == the full matrix."""
+    pos, quat, dim, chi, _ = random_cells(100, seed=11)
+    n, N = 100, 300
+    full = assemble_numpy(ctx, pos, quat, dim, chi_cell_major=chi.reshape(-1))
+    d_pos, d_quat, d_dim, d_chi = (dev(ctx, a) for a in (pos, quat, dim, chi.reshape(-1)))
+    tgt_block, nparts = 8, 3
+    nblk = -(-n // tgt_block)
+    rebuilt = np.zeros_like(full)
+    for part in range(nparts):
+        blocks = list(range(part, nblk, nparts))
+        cells = np.concatenate([np.arange(b * tgt_block, min(n, (b + 1) * tgt_block)) for b in blocks])
+        out = ctx.empty(3 * len(cells), 304)
+        ctx.assemble(d_pos, d_quat, d_dim, out, 304, chi=d_chi, n_tgt_local=len(cells), tgt_block=tgt_block,
+                     tgt_nparts=nparts, tgt_part=part)
+        ctx.sync()
+        loc = out[:, :N].cpu().numpy()
+        rows = (3 * cells[:, None] + np.arange(3)[None, :]).reshape(-1)
+        rebuilt[rows] = loc
+    np.testing.assert_array_equal(rebuilt, full)
+
+
+# ---------------------------------------------------------------------------------------
+# field kernel
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field", ["B", "H"])
+def test_field_kernel_vs_oracle(ctx, field):
+    pos, quat, dim, _, pol = random_cells(150, seed=2)
+    rng = np.random.default_rng(9)
+    obs = np.vstack([rng.uniform(-2e-3, 2e-3, (200, 3)), pos[:5], pos[:5] + dim[:5] * 0.25])
+    ref = ocf.getBH_collection(field, obs, pos, quat, dim, pol)
+    out = ctx.empty(len(obs), 3)
+    ctx.field(dev(ctx, pos), dev(ctx, quat), dev(ctx, dim), dev(ctx, pol), dev(ctx, obs), out,
+              _native.FIELD_B if field == "B" else _native.FIELD_H)
+    got = out.cpu().numpy()
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12 * scale)
+
+
+# ---------------------------------------------------------------------------------------
+# kernel 2a: DGEMM (DMMA) and LU
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize(("m", "n", "k"), [(128, 64, 16), (200, 130, 48), (777, 333, 128), (64, 64, 7), (1500, 1100, 128)])
+def test_dgemm_dmma_vs_fp64_reference(ctx, m, n, k):
+    rng = np.random.default_rng(m + n + k)
+    A = rng.normal(size=(m, k))
+    B = rng.normal(size=(k, n))
+    C = rng.normal(size=(m, n))
+    lda, ldb, ldc = m + 2, k + 4, m + 6
+    # column-major buffers with padding
+    dA = torch.zeros(k, lda, dtype=torch.float64, device=ctx.device)
+    dA[:, :m] = dev(ctx, A.T)
+    dB = torch.zeros(n, ldb, dtype=torch.float64, device=ctx.device)
+    dB[:, :k] = dev(ctx, B.T)
+    dC = torch.zeros(n, ldc, dtype=torch.float64, device=ctx.device)
+    dC[:, :m] = dev(ctx, C.T)
+    ctx.dgemm_nn(m, n, k, -1.0, dA, lda, dB, ldb, 1.0, dC, ldc)
+    ctx.sync()
+    got = dC[:, :m].cpu().numpy().T
+    ref = C - A @ B
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12 * np.sqrt(k))
+    assert torch.all(dC[:, m:] == 0)  # padding untouched
+
+
+@pytest.mark.parametrize("N", [1, 5, 16, 130, 777, 1000, 2049])
+def test_lu_solve_random_dense_vs_numpy(ctx, N):
+    """General (non diagonally dominant) matrices: partial pivoting is required."""
+    rng = np.random.default_rng(N)
+    Q = rng.normal(size=(N, N))
+    b = rng.normal(size=(N,))
+    ld = (N + 15) // 16 * 16
+    dQ = torch.zeros(N, ld, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    ipiv = torch.zeros(N, dtype=torch.int32, device=ctx.device)
+    info = ctx.lu_factor(dQ, ld, ipiv)
+    assert info == 0
+    dx = dev(ctx, b)
+    ctx.lu_solve(dQ, ld, ipiv, dx)
+    x = dx.cpu().numpy()
+    ref = np.linalg.solve(Q, b)
+    resid = np.linalg.norm(Q @ x - b) / (np.linalg.norm(Q) * np.linalg.norm(x))
+    assert resid < 1e-14, resid
+    cond = np.linalg.cond(Q)
+    np.testing.assert_allclose(x, ref, rtol=0, atol=1e-13 * cond * np.abs(ref).max())
+    # pivots are a valid LAPACK-style sequence
+    p = ipiv.cpu().numpy()
+    assert np.all(p >= np.arange(N)) and np.all(p < N)
+
+
+def test_lu_reports_singular_matrix(ctx):
+    N = 40
+    Q = np.random.default_rng(0).normal(size=(N, N))
+    Q[:, 7] = 0.0  # zero column of Q = zero row of Q^T
+    Q[7, :] = 0.0
+    dQ = torch.zeros(N, 48, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    ipiv = torch.zeros(N, dtype=torch.int32, device=ctx.device)
+    assert ctx.lu_factor(dQ, 48, ipiv) > 0
+
+
+# ---------------------------------------------------------------------------------------
+# kernel 2b: GMRES
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize(("N", "restart"), [(300, 50), (1001, 20)])
+def test_gmres_vs_numpy_solve(ctx, N, restart):
+    rng = np.random.default_rng(N)
+    Q = np.eye(N) + 0.5 * rng.normal(size=(N, N)) / np.sqrt(N)
+    b = rng.normal(size=(N,))
+    ld = (N + 15) // 16 * 16
+    dQ = torch.zeros(N, ld, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    db = dev(ctx, b)
+    dx = torch.zeros_like(db)
+    iters, relres = ctx.gmres(dQ, ld, db, dx, tol=1e-13, restart=restart, maxit=500)
+    assert relres <= 1e-13 and 0 < iters < 500
+    np.testing.assert_allclose(dx.cpu().numpy(), np.linalg.solve(Q, b), rtol=1e-10, atol=1e-12)
+    # matvec export
+    dy = torch.zeros_like(db)
+    ctx.matvec(dQ, ld, dx, dy)
+    np.testing.assert_allclose(dy.cpu().numpy(), b, rtol=1e-11, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------
+# end to end through the reference-facing API
+# ---------------------------------------------------------------------------------------
+ANSYS_CASES = [
+    ("isotropic_results_ansys.txt", (0, 0, 1.1), 0.1, 0.0012),
+    ("anisotropic_results_ansys.txt", (0, 0, 1.1), (0.3, 0.2, 0.1), 0.0012),
+    ("negative_susceptibility_ansys.txt", (0, 0, -0.1), -1.1, 0.0065),
+]
+
+
+@pytest.mark.parametrize("solver", ["lu", "gmres"])
+@pytest.mark.parametrize(("fname", "J", "chi", "atol"), ANSYS_CASES)
+def test_reference_ansys_goldens_through_the_api(golden_dir, fname, J, chi, atol, solver):
+    """The reference's own tests (tests/test_isotropic_anisotropic.py:9-67), verbatim flow:
+    Cuboid -> mesh_Cuboid(1000) -> apply_demag(inplace) -> getB(grid) vs ANSYS."""
+    magnet = Cuboid(dimension=(1e-3, 1e-3, 1e-3), polarization=J)
+    grid = np.loadtxt(golden_dir / "ansys" / "grid_points.pts")
+    field_ansys = np.loadtxt(golden_dir / "ansys" / fname, skiprows=1)[:, 3:]
+    magnet.susceptibility = chi
+    meshed = mesh_Cuboid(magnet, 1000)
+    assert apply_demag(meshed, inplace=True, solver=solver) is None
+    field = meshed.getB(grid)
+    np.testing.assert_allclose(field_ansys, field, rtol=0, atol=atol)
+    # and tight parity with the oracle on the same mesh (config 1)
+    pos, quat, dim = oref.mesh_cuboid_arrays((1e-3,) * 3, 1000)
+    ref = oref.apply_demag_ref(pos, quat, dim, np.tile(np.asarray(J, float), (1000, 1)), chi)
+    got = np.array([s.polarization for s in meshed.sources_all])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.all(np.abs(got - ref) <= J_RTOL * scale)
+
+
+def test_apply_demag_integration_equivalent_susceptibility_inputs():
+    """tests/test_basic.py:16-32 + the SURVEY 8c small known answer."""
+    zone = Cuboid(dimension=(1, 1, 1), polarization=(0, 0, 1))
+    mesh = mesh_Cuboid(zone, (2, 2, 2))
+    dm1 = apply_demag(mesh, susceptibility=4)
+    dm2 = apply_demag(mesh, susceptibility=(4, 4, 4))
+    zone.susceptibility = 4
+    dm3 = apply_demag(mesh_Cuboid(zone, (2, 2, 2)))
+    b_ref = dm1.getB((1, 2, 3))
+    np.testing.assert_allclose(dm2.getB((1, 2, 3)), b_ref)
+    np.testing.assert_allclose(dm3.getB((1, 2, 3)), b_ref)
+    np.testing.assert_allclose(b_ref, (4.2419262588694e-4, 8.4895681674371e-4, 6.1656992445783e-4), rtol=1e-10)
+    J = np.array([s.polarization for s in dm1.sources_all])
+    np.testing.assert_allclose(J[:, 2], 0.435700173485776, rtol=1e-11)
+    # input not mutated when inplace=False
+    assert all(np.array_equal(s.polarization, (0, 0, 1)) for s in mesh.sources_all)
+
+
+@pytest.mark.parametrize("solver", ["lu", "gmres"])
+@pytest.mark.parametrize("mode", ["plain", "split", "pairs_matching", "max_dist"])
+def test_apply_demag_two_magnets_rotated_soft_iron_vs_oracle(solver, mode):
+    """Config 2 at reduced size (2 x 6x6x3 cells): hard magnet chi=0.5 + soft cube chi=1000 rotated
+    45 deg about y, with H_ext on the soft part; all assembly modes of the reference API."""
+    hard = Cuboid(polarization=(0, 0, 1), dimension=(1e-3, 1e-3, 2e-3), position=(0, 0, 0.5e-3))
+    hard.susceptibility = 0.5
+    soft = Cuboid(polarization=(0, 0, 0), dimension=(1e-3, 1e-3, 1e-3))
+    soft.rotate_from_angax(45, "y").move((1.5e-3, 0, 0))
+    soft.susceptibility = 1000
+    mh, ms = mesh_Cuboid(hard, (6, 6, 3)), mesh_Cuboid(soft, (6, 6, 3))
+    ms.H_ext = (0.0, 0.1, 0.2)
+    coll = Collection(mh, ms)
+    kw = {"plain": {}, "split": {"split": 7}, "pairs_matching": {"pairs_matching": True}, "max_dist": {"max_dist": 6.0}}[mode]
+    out = apply_demag(coll, solver=solver, **kw)
+    srcs = coll.sources_all
+    pos, quat, dim = _cell_geometry(srcs)
+    n = len(srcs)
+    pol = np.array([s.polarization for s in srcs])
+    chi = np.array([[0.5] * 3] * (n // 2) + [[1000.0] * 3] * (n // 2))
+    H_ext = np.array([[0.0, 0, 0]] * (n // 2) + [[0.0, 0.1, 0.2]] * (n // 2))
+    okw = {"max_dist": 6.0} if mode == "max_dist" else {}
+    ref = oref.apply_demag_ref(pos, quat, dim, pol, chi, H_ext=H_ext, **okw)
+    got = np.array([s.polarization for s in out.sources_all])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.all(np.abs(got - ref) <= J_RTOL * scale), np.abs(got - ref).max()
+
+
+def test_apply_demag_random_anisotropic_stress_vs_oracle():
+    pos, quat, dim, chi, pol = random_cells(512, seed=0)
+    chi = np.abs(chi) * 0.2  # keep Q comfortably non-singular for a tight comparison
+    cells = []
+    for i in range(len(pos)):
+        c = Cuboid(position=pos[i], orientation=R.from_quat(quat[i]), dimension=dim[i], polarization=pol[i])
+        c.susceptibility = tuple(chi[i])
+        cells.append(c)
+    out = apply_demag(Collection(cells))
+    ref = oref.apply_demag_ref(pos, quat, dim, pol, chi)
+    got = np.array([s.polarization for s in out.sources_all])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.all(np.abs(got - ref) <= J_RTOL * scale), np.abs(got - ref).max()
+
+
+# ---------------------------------------------------------------------------------------
+# full BASELINE size (n = 8000, N = 24000): size-independent properties
+# ---------------------------------------------------------------------------------------
+def test_config2prime_8000_cells_properties(ctx):
+    """North-star target config: soft-iron cube 20x20x20, chi=1000, H_ext=(0,0,1)."""
+    cube = Cuboid(dimension=(1e-3,) * 3, polarization=(0, 0, 0))
+    cube.susceptibility = 1000
+    mesh = mesh_Cuboid(cube, (20, 20, 20))
+    mesh.H_ext = (0.0, 0.0, 1.0)
+    n, N = 8000, 24000
+    pos, quat, dim = _cell_geometry(mesh.sources_all)
+    # (1) tensor: trace of every self block is -1; symmetric for identical cells; rows sum rule
+    Nmat, ld = _assemble_device(ctx, pos, quat, dim)
+    A = Nmat[:, :N]
+    assert abs(float(torch.diagonal(A).sum()) + n) < 1e-9
+    assert float((A - A.T).abs().max()) < 4e-15  # 2x the closed form's absolute error
+    # translation invariance: block (i, j) depends on the displacement only
+    blk = A.reshape(n, 3, n, 3)
+    np.testing.assert_allclose(blk[0, :, 1, :].cpu().numpy(), blk[400, :, 401, :].cpu().numpy(), rtol=1e-12, atol=2e-15)
+    # spot-check 64 random rows against the oracle
+    rng = np.random.default_rng(1)
+    jj = rng.choice(n, 8, replace=False)
+    H = np.stack([
+        ocf.getBH_cuboid_sources("H", pos[jj], pos, quat, dim, np.tile(np.eye(3)[k], (n, 1))) for k in range(3)
+    ])  # [k, i, jsel, l]
+    ref_rows = ocf.MU0 * H.transpose(2, 3, 1, 0).reshape(len(jj) * 3, N)  # [(jsel,l), (i,k)]
+    rows = (3 * jj[:, None] + np.arange(3)[None, :]).reshape(-1)
+    assert_T_close(A[rows].cpu().numpy(), ref_rows)
+    del Nmat, A, blk
+    # (2) solve: both solvers agree with each other and satisfy the system
+    out_lu, info_lu = apply_demag(mesh, solver="lu", return_info=True)
+    out_gm, info_gm = apply_demag(mesh, solver="gmres", return_info=True)
+    J_lu = np.array([s.polarization for s in out_lu.sources_all])
+    J_gm = np.array([s.polarization for s in out_gm.sources_all])
+    assert np.abs(J_lu - J_gm).max() <= J_RTOL * np.abs(J_lu).max()
+    assert info_gm["gmres_relres"] <= 1e-12
+    chi = np.full(N, 1000.0)
+    Q, ld = _assemble_device(ctx, pos, quat, dim, chi_cell_major=chi)
+    x = torch.from_numpy(J_lu.reshape(-1)).to(ctx.device)
+    y = torch.empty_like(x)
+    ctx.matvec(Q, ld, x, y)
+    rhs = np.tile((0.0, 0.0, 1000.0), n)
+    resid = np.linalg.norm(y.cpu().numpy() - rhs) / np.linalg.norm(rhs)
+    assert resid < 1e-11, resid
+    # physics: mean J_z between the n=1000 (3.5716) and n=2744 (3.5948) values of SURVEY 8c, x/y vanish
+    assert 3.55 < J_lu[:, 2].mean() < 3.65
+    assert abs(J_lu[:, 0].mean()) < 1e-9
