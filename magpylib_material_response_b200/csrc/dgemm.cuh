@@ -42,7 +42,11 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // ALIGNED16: A, B 16-byte aligned with even leading dimensions (cp.async 16 B); otherwise 8 B.
-template <bool ALIGNED16>
+// SUBTRACT : the LU form C <- C - A*B (alpha = -1, beta = 1).  The C tile is loaded straight into
+//            the accumulators (negated) BEFORE the main loop, so its DRAM latency overlaps the
+//            cp.async prologue and the epilogue is store-only.  (ncu on the first version showed
+//            50% of all stall samples on the epilogue's C loads.)
+template <bool ALIGNED16, bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                     const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
@@ -66,6 +70,20 @@ __global__ void __launch_bounds__(THREADS, 2)
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT = (k + BK - 1) / BK;
+
+  if (SUBTRACT) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int gm = m0 + wm * 32 + 8 * f + (lane >> 2);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
+          if (gm < m && gn < n) acc[f][g][e] = -__ldcs(C + (int64_t)gn * ldc + gm);
+        }
+    }
+  }
 
   auto load_tile = [&](int stage, int kt) {
     const int k0 = kt * BK;
@@ -164,8 +182,12 @@ __global__ void __launch_bounds__(THREADS, 2)
         const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
         if (gn < n) {
           double* cp = C + (int64_t)gn * ldc + gm;
-          const double v = alpha * acc[f][g][e];
-          *cp = (beta == 0.0) ? v : (v + beta * (*cp));
+          if (SUBTRACT) {
+            *cp = -acc[f][g][e];
+          } else {
+            const double v = alpha * acc[f][g][e];
+            *cp = (beta == 0.0) ? v : (v + beta * (*cp));
+          }
         }
       }
     }

@@ -186,6 +186,392 @@ __global__ void __launch_bounds__(STRIP_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------
+// Cluster variant of the strip factorization: ONE thread-block cluster (<= 16 CTAs) holds the
+// whole strip in distributed shared memory.  The per-column pivot search uses the hardware
+// cluster barrier and DSMEM reads of the other CTAs' candidates instead of a grid-wide software
+// barrier through L2 (measured 4.8 us per column with the cooperative-grid kernel above).
+// Used whenever rows x W doubles fit 16 x 200 KB (N <= ~25600 at W = 16; always in the late
+// panels of larger matrices).
+// ---------------------------------------------------------------------------------------
+constexpr int CSTRIP_THREADS = 512;
+
+struct StripRec {
+  double absval;
+  int row;
+  int pad;
+  double vals[W];
+};
+
+__global__ void __launch_bounds__(CSTRIP_THREADS)
+    lu_strip_cluster_kernel(double* __restrict__ A, int64_t ld, int N, int c0, int w, int rows_per,
+                            int* __restrict__ ipiv, int* __restrict__ info) {
+  extern __shared__ __align__(16) double S[];  // [W][rows_per]
+  __shared__ StripRec rec[2];
+  __shared__ double diag[2][W];
+  __shared__ double s_red_val[CSTRIP_THREADS / 32];
+  __shared__ int s_red_row[CSTRIP_THREADS / 32];
+  __shared__ double s_prow[W];
+  __shared__ int s_piv_row;
+  __shared__ int s_piv_cta;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int G = (int)cluster.num_blocks();
+  const int cta = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int m = N - c0;
+  const int r_begin = cta * rows_per;
+  const int r_cnt = max(0, min(rows_per, m - r_begin));
+
+  for (int c = 0; c < w; ++c) {
+    const double* src = A + (int64_t)(c0 + c) * ld + c0 + r_begin;
+    for (int r = tid; r < r_cnt; r += CSTRIP_THREADS) S[c * rows_per + r] = src[r];
+  }
+  __syncthreads();
+
+  for (int jj = 0; jj < w; ++jj) {
+    const int buf = jj & 1;
+    double best = -1.0;
+    int best_row = 0x7fffffff;
+    const int lo = max(0, jj - r_begin);
+    for (int r = lo + tid; r < r_cnt; r += CSTRIP_THREADS) {
+      const double v = fabs(S[jj * rows_per + r]);
+      if (v > best) {
+        best = v;
+        best_row = r_begin + r;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, best, off);
+      const int orow = __shfl_down_sync(0xffffffffu, best_row, off);
+      if (ov > best || (ov == best && orow < best_row)) {
+        best = ov;
+        best_row = orow;
+      }
+    }
+    if ((tid & 31) == 0) {
+      s_red_val[tid >> 5] = best;
+      s_red_row[tid >> 5] = best_row;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      best = (tid < CSTRIP_THREADS / 32) ? s_red_val[tid] : -1.0;
+      best_row = (tid < CSTRIP_THREADS / 32) ? s_red_row[tid] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int orow = __shfl_down_sync(0xffffffffu, best_row, off);
+        if (ov > best || (ov == best && orow < best_row)) {
+          best = ov;
+          best_row = orow;
+        }
+      }
+      best = __shfl_sync(0xffffffffu, best, 0);
+      best_row = __shfl_sync(0xffffffffu, best_row, 0);
+      if (tid == 0) {
+        rec[buf].absval = best;
+        rec[buf].row = best_row;
+      }
+      const int lr = best_row - r_begin;
+      if (tid < w && best_row != 0x7fffffff) rec[buf].vals[tid] = S[tid * rows_per + lr];
+      if (cta == 0 && tid < w) diag[buf][tid] = S[tid * rows_per + jj];
+    }
+    cluster.sync();  // release/acquire: every CTA's record is visible cluster-wide
+
+    if (tid < 32) {
+      double bv = -1.0;
+      int br = 0x7fffffff, bc = 0;
+      if (tid < G) {
+        const StripRec* rr = cluster.map_shared_rank(&rec[buf], tid);
+        bv = rr->absval;
+        br = rr->row;
+        bc = tid;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int orow = __shfl_down_sync(0xffffffffu, br, off);
+        const int oc = __shfl_down_sync(0xffffffffu, bc, off);
+        if (ov > bv || (ov == bv && orow < br)) {
+          bv = ov;
+          br = orow;
+          bc = oc;
+        }
+      }
+      br = __shfl_sync(0xffffffffu, br, 0);
+      bc = __shfl_sync(0xffffffffu, bc, 0);
+      if (tid == 0) {
+        s_piv_row = br;
+        s_piv_cta = bc;
+      }
+      if (tid < w) {
+        const StripRec* rr = cluster.map_shared_rank(&rec[buf], bc);
+        s_prow[tid] = rr->vals[tid];
+      }
+    }
+    __syncthreads();
+    const int prow = s_piv_row;
+    const int pcta = s_piv_cta;
+    if (prow != jj) {
+      if (cta == pcta && tid < w) {
+        const double* dg = cluster.map_shared_rank(&diag[buf][0], 0);
+        S[tid * rows_per + (prow - r_begin)] = dg[tid];
+      }
+      __syncthreads();
+      if (cta == 0 && tid < w) S[tid * rows_per + jj] = s_prow[tid];
+    }
+    if (cta == 0 && tid == 0) {
+      ipiv[c0 + jj] = c0 + prow;
+      if (s_prow[jj] == 0.0) atomicCAS(info, 0, c0 + jj + 1);
+    }
+    __syncthreads();
+    const double piv = s_prow[jj];
+    if (piv != 0.0) {
+      const double rinv = 1.0 / piv;
+      const int lo2 = max(0, jj + 1 - r_begin);
+      for (int r = lo2 + tid; r < r_cnt; r += CSTRIP_THREADS) {
+        const double l = S[jj * rows_per + r] * rinv;
+        S[jj * rows_per + r] = l;
+        for (int c = jj + 1; c < w; ++c) S[c * rows_per + r] -= l * s_prow[c];
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = 0; c < w; ++c) {
+    double* dst = A + (int64_t)(c0 + c) * ld + c0 + r_begin;
+    for (int r = tid; r < r_cnt; r += CSTRIP_THREADS) dst[r] = S[c * rows_per + r];
+  }
+  cluster.sync();  // nobody may exit while its shared memory can still be read remotely
+}
+
+// ---------------------------------------------------------------------------------------
+// Register-resident cluster strip kernel: every thread keeps RPT rows x W columns of the strip
+// in registers, so the rank-1 updates are pure register DFMAs.  Each CTA PUSHES its pivot
+// candidate (|value|, row, the row's W values) into every CTA's shared-memory inbox through
+// DSMEM before the cluster barrier; after the barrier all pivot data is local.  The barrier is
+// split (arrive.release ... wait.acquire).  One barrier per column, no global-memory traffic
+// inside the column loop.
+// ---------------------------------------------------------------------------------------
+constexpr int RSTRIP_THREADS = 512;
+constexpr int MAX_CLUSTER = 16;
+
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(RSTRIP_THREADS, 1)
+    lu_strip_reg_kernel(double* __restrict__ A, int64_t ld, int N, int c0, int w, int rows_per,
+                        int* __restrict__ ipiv, int* __restrict__ info) {
+  __shared__ StripRec inbox[2][MAX_CLUSTER];
+  __shared__ double diagbox[2][W];
+  __shared__ StripRec mine;
+  __shared__ double mydiag[W];
+  __shared__ double s_red_val[RSTRIP_THREADS / 32];
+  __shared__ int s_red_row[RSTRIP_THREADS / 32];
+  __shared__ double s_prow[W];
+  __shared__ int s_piv_row;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int G = (int)cluster.num_blocks();
+  const int cta = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const int m = N - c0;
+  const int r_begin = cta * rows_per;
+  const int r_cnt = max(0, min(rows_per, m - r_begin));
+
+  double a[RPT][W];
+  int rowidx[RPT];  // panel-relative row, or -1
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int lr = tid + RSTRIP_THREADS * i;
+    rowidx[i] = (lr < r_cnt) ? (r_begin + lr) : -1;
+#pragma unroll
+    for (int c = 0; c < W; ++c)
+      a[i][c] = (rowidx[i] >= 0 && c < w) ? A[(int64_t)(c0 + c) * ld + c0 + rowidx[i]] : 0.0;
+  }
+  // all CTAs of the cluster must be running before anyone writes into a remote inbox
+  cluster_arrive_release();
+  cluster_wait_acquire();
+
+  // Column loop, NOT unrolled (a fully unrolled body is ~180 KB of code that is executed once per
+  // launch: the first version was instruction-cache-miss bound).  The register columns are
+  // rotated by one after every step so the current column is always a[.][0]; positions
+  // 1 .. w-1-jj hold the columns still to be updated, the rest already-final L columns.
+#pragma unroll 1
+  for (int jj = 0; jj < w; ++jj) {
+    const int buf = jj & 1;
+    // 1. local candidate
+    double best = -1.0;
+    int best_row = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const double v = fabs(a[i][0]);
+      if (rowidx[i] >= jj && v > best) {
+        best = v;
+        best_row = rowidx[i];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, best, off);
+      const int orow = __shfl_down_sync(0xffffffffu, best_row, off);
+      if (ov > best || (ov == best && orow < best_row)) {
+        best = ov;
+        best_row = orow;
+      }
+    }
+    if ((tid & 31) == 0) {
+      s_red_val[tid >> 5] = best;
+      s_red_row[tid >> 5] = best_row;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      best = (tid < RSTRIP_THREADS / 32) ? s_red_val[tid] : -1.0;
+      best_row = (tid < RSTRIP_THREADS / 32) ? s_red_row[tid] : 0x7fffffff;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int orow = __shfl_down_sync(0xffffffffu, best_row, off);
+        if (ov > best || (ov == best && orow < best_row)) {
+          best = ov;
+          best_row = orow;
+        }
+      }
+      if (tid == 0) {
+        mine.absval = best;
+        mine.row = best_row;
+      }
+    }
+    __syncthreads();
+    // owner threads deposit the candidate row and (CTA 0) the current diagonal row
+    {
+      const int cand_row = mine.row;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        if (rowidx[i] == cand_row && cand_row != 0x7fffffff) {
+#pragma unroll
+          for (int c = 0; c < W; ++c) mine.vals[c] = a[i][c];
+        }
+        if (rowidx[i] == jj) {
+#pragma unroll
+          for (int c = 0; c < W; ++c) mydiag[c] = a[i][c];
+        }
+      }
+    }
+    __syncthreads();
+    // 2. push my record into every CTA's inbox (DSMEM stores), then the cluster barrier
+    {
+      constexpr int REC_WORDS = sizeof(StripRec) / 8;  // 18
+      const int wd = tid & 31;
+      for (int dst = tid / 32; dst < G; dst += RSTRIP_THREADS / 32) {  // one warp per destination CTA
+        StripRec* remote = cluster.map_shared_rank(&inbox[buf][cta], dst);
+        if (wd < REC_WORDS) reinterpret_cast<double*>(remote)[wd] = reinterpret_cast<const double*>(&mine)[wd];
+        if (cta == 0 && wd < W) {
+          double* rd = cluster.map_shared_rank(&diagbox[buf][0], dst);
+          rd[wd] = mydiag[wd];
+        }
+      }
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    // 3. winner (local data only)
+    if (tid < 32) {
+      double bv = -1.0;
+      int br = 0x7fffffff, bc = 0;
+      if (tid < G) {
+        bv = inbox[buf][tid].absval;
+        br = inbox[buf][tid].row;
+        bc = tid;
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int orow = __shfl_down_sync(0xffffffffu, br, off);
+        const int oc = __shfl_down_sync(0xffffffffu, bc, off);
+        if (ov > bv || (ov == bv && orow < br)) {
+          bv = ov;
+          br = orow;
+          bc = oc;
+        }
+      }
+      br = __shfl_sync(0xffffffffu, br, 0);
+      bc = __shfl_sync(0xffffffffu, bc, 0);
+      if (tid == 0) s_piv_row = br;
+      if (tid < W) s_prow[tid] = inbox[buf][bc].vals[tid];
+    }
+    __syncthreads();
+    const int prow = s_piv_row;
+    // 4. swap rows jj <-> prow (inside the registers of their owner threads)
+    if (prow != jj) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        if (rowidx[i] == prow) {
+#pragma unroll
+          for (int c = 0; c < W; ++c) a[i][c] = diagbox[buf][c];
+        } else if (rowidx[i] == jj) {
+#pragma unroll
+          for (int c = 0; c < W; ++c) a[i][c] = s_prow[c];
+        }
+      }
+    }
+    if (cta == 0 && tid == 0) {
+      ipiv[c0 + jj] = c0 + prow;
+      if (s_prow[0] == 0.0) atomicCAS(info, 0, c0 + jj + 1);
+    }
+    // 5. scale + rank-1 update fused with the rotation: a[.][c-1] <- a[.][c] - l * prow[c]
+    const double piv = s_prow[0];
+    const double rinv = (piv != 0.0) ? 1.0 / piv : 0.0;
+    const int nright = w - jj;  // positions 1 .. nright-1 are still to be updated
+    double l[RPT], keep[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const bool act = rowidx[i] > jj && piv != 0.0;
+      l[i] = act ? a[i][0] * rinv : 0.0;
+      keep[i] = act ? l[i] : a[i][0];
+    }
+#pragma unroll
+    for (int c = 1; c < W; ++c) {
+      const double pc = (c < nright) ? s_prow[c] : 0.0;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) a[i][c - 1] = a[i][c] - l[i] * pc;
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) a[i][W - 1] = keep[i];
+    // s_prow / mine / mydiag are rewritten only after the next column's first __syncthreads
+  }
+  // undo the remaining rotation (w < W only) so a[.][c] is column c again
+  for (int extra = w; extra < W; ++extra) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const double t = a[i][0];
+#pragma unroll
+      for (int c = 0; c < W - 1; ++c) a[i][c] = a[i][c + 1];
+      a[i][W - 1] = t;
+    }
+  }
+  double* Aw = A;
+  asm volatile("" : "+l"(Aw));  // fresh address arithmetic: do not keep 16 x RPT pointers live
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    if (rowidx[i] >= 0) {
+      double* dst = Aw + (int64_t)c0 * ld + c0 + rowidx[i];
+#pragma unroll
+      for (int c = 0; c < W; ++c) {
+        if (c < w) *dst = a[i][c];
+        dst += ld;
+      }
+    }
+  }
+  // nobody may exit while a peer can still write into its inbox
+  cluster_arrive_release();
+  cluster_wait_acquire();
+}
+
+// ---------------------------------------------------------------------------------------
 // After a strip [c0, c0+w) is factored: apply its row swaps to the other panel columns
 // [pc0, c0) and [c0+w, pc1), and for the right part also solve with the strip's unit-lower
 // W x W block (rows c0..c0+w of those columns become rows of U).  One thread per column.
@@ -275,14 +661,40 @@ __global__ void __launch_bounds__(256)
     Ls[c * (nb + 1) + r] = (r > c) ? L[(int64_t)c * ldl + r] : 0.0;
   }
   __syncthreads();
-  // thread -> (column c = tid % TRSM_COLS, row group rg = tid / TRSM_COLS of 8 groups)
+  // Blocked forward substitution, TB rows at a time: (i) one thread per column solves the TB x TB
+  // unit-lower diagonal block from registers, (ii) all threads apply the rank-TB update to the rows
+  // below.  2 barriers per TB rows instead of 1 per row.
+  constexpr int TB = 16;
   const int c = tid % TRSM_COLS;
   const int rg = tid / TRSM_COLS;
   constexpr int RG = 256 / TRSM_COLS;
-  for (int t = 0; t < nb - 1; ++t) {
-    const double bt = Bs[c * (nb + 1) + t];
-    if (c < nc) {
-      for (int r = t + 1 + rg; r < nb; r += RG) Bs[c * (nb + 1) + r] -= Ls[t * (nb + 1) + r] * bt;
+  for (int t0 = 0; t0 < nb; t0 += TB) {
+    const int tb = min(TB, nb - t0);
+    if (tid < nc) {
+      double x[TB];
+#pragma unroll
+      for (int i = 0; i < TB; ++i) x[i] = (i < tb) ? Bs[tid * (nb + 1) + t0 + i] : 0.0;
+#pragma unroll
+      for (int i = 1; i < TB; ++i) {
+#pragma unroll
+        for (int q = 0; q < i; ++q)
+          if (i < tb) x[i] -= Ls[(t0 + q) * (nb + 1) + t0 + i] * x[q];
+      }
+#pragma unroll
+      for (int i = 0; i < TB; ++i)
+        if (i < tb) Bs[tid * (nb + 1) + t0 + i] = x[i];
+    }
+    __syncthreads();
+    if (c < nc && t0 + tb < nb) {
+      double x[TB];
+#pragma unroll
+      for (int i = 0; i < TB; ++i) x[i] = (i < tb) ? Bs[c * (nb + 1) + t0 + i] : 0.0;
+      for (int r = t0 + tb + rg; r < nb; r += RG) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < TB; ++q) acc += Ls[(t0 + q) * (nb + 1) + r] * x[q];
+        Bs[c * (nb + 1) + r] -= acc;
+      }
     }
     __syncthreads();
   }
@@ -361,24 +773,20 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
                      double* C, int64_t ldc) {
   using namespace mmr_gemm;
   if (m <= 0 || n <= 0) return 0;
-  static bool attr_set[2] = {false, false};
   const bool aligned = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
-  if (!attr_set[aligned]) {
-    if (aligned)
-      MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)SMEM_BYTES));
-    else
-      MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)SMEM_BYTES));
-    attr_set[aligned] = true;
+  const bool subtract = (alpha == -1.0 && beta == 1.0);
+  typedef void (*kern_t)(int, int, int, double, const double*, int64_t, const double*, int64_t, double,
+                         double*, int64_t);
+  static const kern_t kerns[4] = {dgemm_nn_kernel<false, false>, dgemm_nn_kernel<false, true>,
+                                  dgemm_nn_kernel<true, false>, dgemm_nn_kernel<true, true>};
+  static bool attr_set[4] = {false, false, false, false};
+  const int which = (aligned ? 2 : 0) + (subtract ? 1 : 0);
+  if (!attr_set[which]) {
+    MMR_CUDA(cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set[which] = true;
   }
   dim3 grid((unsigned)ceil_div64(m, BM), (unsigned)ceil_div64(n, BN));
-  if (aligned)
-    dgemm_nn_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb,
-                                                           beta, C, ldc);
-  else
-    dgemm_nn_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B,
-                                                            ldb, beta, C, ldc);
+  kerns[which]<<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -406,27 +814,114 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
                                   (int)strip_smem_cap));
     max_coop_ctas = ctx->sm_count;  // 1 CTA per SM at up to 200 KB of shared memory
   }
+  static bool reg_ok = false;
+  static int cluster_max = -1;  // largest launchable cluster size for the cluster strip kernel
+  if (cluster_max < 0) {
+    cluster_max = 0;
+    if (cudaFuncSetAttribute(lu_strip_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)strip_smem_cap) == cudaSuccess &&
+        cudaFuncSetAttribute(lu_strip_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
+            cudaSuccess) {
+      for (int cs = 16; cs >= 1; cs >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(CSTRIP_THREADS);
+        cfg.dynamicSmemBytes = strip_smem_cap;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, lu_strip_cluster_kernel, &cfg) == cudaSuccess &&
+            nclusters >= 1) {
+          cluster_max = cs;
+          break;
+        }
+      }
+    }
+    cudaGetLastError();  // clear any probe error
+    reg_ok = cudaFuncSetAttribute(lu_strip_reg_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+             cudaFuncSetAttribute(lu_strip_reg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+             cudaFuncSetAttribute(lu_strip_reg_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+  }
   Cand* cand = (Cand*)d_scratch;
   double* candrow = (double*)((char*)d_scratch + 2 * 256 * sizeof(Cand));
   double* diagrow = candrow + 2 * 256 * W;
   for (int c0 = kb; c0 < kb + nb; c0 += W) {
     const int w = min(W, kb + nb - c0);
     const int m = N - c0;
-    int G = min(max_coop_ctas, max(1, m / MIN_ROWS_PER_CTA));
-    int rows_per = (int)ceil_div64(m, G);
-    rows_per = max(rows_per, W);
-    rows_per = (rows_per + 1) & ~1;
-    G = (int)ceil_div64(m, rows_per);
-    const size_t smem = (size_t)W * rows_per * sizeof(double);
-    if (smem > strip_smem_cap) {
-      mmr_set_error("LU strip of %d rows does not fit the distributed shared memory (%zu B/CTA)", m, smem);
-      return -5;
-    }
-    int w_arg = w, N_arg = N, c0_arg = c0;
-    void* args[] = {&A, &ld, &N_arg, &c0_arg, &w_arg, &rows_per, &d_ipiv, &cand, &candrow, &diagrow, &d_info};
     const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, ctx->stream);
-    MMR_CUDA(cudaLaunchCooperativeKernel((void*)lu_strip_kernel, dim3(G), dim3(STRIP_THREADS), args, smem,
-                                         ctx->stream));
+    // cluster path: smallest power-of-two cluster that keeps >= 128 rows per CTA and fits smem
+    int cs = 0;
+    if (cluster_max >= 1) {
+      cs = 1;
+      while (cs < cluster_max && (m / cs > 256 || (size_t)W * ((m + cs - 1) / cs + 2) * sizeof(double) > strip_smem_cap))
+        cs <<= 1;
+      int rp = max((int)ceil_div64(m, cs), W);
+      rp = (rp + 1) & ~1;
+      if ((size_t)W * rp * sizeof(double) > strip_smem_cap) cs = 0;
+    }
+    // register-resident variant: rows per CTA <= RSTRIP_THREADS * 3
+    int csr = 0;
+    if (cluster_max >= 1 && reg_ok) {
+      csr = 1;
+      while (csr < cluster_max && m / csr > 512) csr <<= 1;
+      if ((int)ceil_div64(m, csr) > RSTRIP_THREADS * 3) csr = 0;
+    }
+    if (csr >= 1) {
+      const int rows_per = max((int)ceil_div64(m, csr), W);
+      const int rpt = (int)ceil_div64(rows_per, RSTRIP_THREADS);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(csr);
+      cfg.blockDim = dim3(RSTRIP_THREADS);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = csr;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (rpt <= 1) MMR_CUDA(cudaLaunchKernelEx(&cfg, lu_strip_reg_kernel<1>, A, ld, N, c0, w, rows_per, d_ipiv, d_info));
+      else if (rpt == 2) MMR_CUDA(cudaLaunchKernelEx(&cfg, lu_strip_reg_kernel<2>, A, ld, N, c0, w, rows_per, d_ipiv, d_info));
+      else MMR_CUDA(cudaLaunchKernelEx(&cfg, lu_strip_reg_kernel<3>, A, ld, N, c0, w, rows_per, d_ipiv, d_info));
+    } else if (cs >= 1) {
+      int rows_per = max((int)ceil_div64(m, cs), W);
+      rows_per = (rows_per + 1) & ~1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs);
+      cfg.blockDim = dim3(CSTRIP_THREADS);
+      cfg.dynamicSmemBytes = (size_t)W * rows_per * sizeof(double);
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      MMR_CUDA(cudaLaunchKernelEx(&cfg, lu_strip_cluster_kernel, A, ld, N, c0, w, rows_per, d_ipiv, d_info));
+    } else {
+      int G = min(max_coop_ctas, max(1, m / MIN_ROWS_PER_CTA));
+      int rows_per = (int)ceil_div64(m, G);
+      rows_per = max(rows_per, W);
+      rows_per = (rows_per + 1) & ~1;
+      G = (int)ceil_div64(m, rows_per);
+      const size_t smem = (size_t)W * rows_per * sizeof(double);
+      if (smem > strip_smem_cap) {
+        mmr_set_error("LU strip of %d rows does not fit the distributed shared memory (%zu B/CTA)", m, smem);
+        return -5;
+      }
+      int w_arg = w, N_arg = N, c0_arg = c0;
+      void* args[] = {&A, &ld, &N_arg, &c0_arg, &w_arg, &rows_per, &d_ipiv, &cand, &candrow, &diagrow, &d_info};
+      MMR_CUDA(cudaLaunchCooperativeKernel((void*)lu_strip_kernel, dim3(G), dim3(STRIP_THREADS), args, smem,
+                                           ctx->stream));
+    }
     mmr_prof_end(ctx, pidx, (double)w, ctx->stream);
     ctx->launches++;
     const int ncol_other = nb - w;
