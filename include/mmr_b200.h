@@ -82,6 +82,8 @@ int64_t mmr_ctx_launch_count(mmr_ctx* ctx);
 int mmr_ctx_set_profiling(mmr_ctx* ctx, int on);
 int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
                     int64_t* launches_out);
+/* Individual record durations (ms) of one class, in launch order; returns the count written. */
+int64_t mmr_ctx_profile_records(mmr_ctx* ctx, int kind, double* ms_out, int64_t cap);
 
 /* ---- kernel 1: demag tensor assembly (demag.py:124-224 + :451-452 + :466) ------------- */
 /*

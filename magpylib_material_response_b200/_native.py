@@ -49,6 +49,10 @@ _SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
          ctypes.POINTER(ctypes.c_int64)],
     ),
+    "mmr_ctx_profile_records": (
+        ctypes.c_int64,
+        [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int64],
+    ),
     "mmr_assemble": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]
@@ -233,6 +237,11 @@ class Context:
                                                       ctypes.byref(cnt)))
             out[name] = (ms.value, units.value, cnt.value)
         return out
+
+    def profile_records(self, kind, cap=100000):
+        buf = (ctypes.c_double * cap)()
+        n = self.lib.mmr_ctx_profile_records(self.handle, self.PROF_KINDS.index(kind), buf, cap)
+        return list(buf[:n])
 
     # ---- kernel 1 --------------------------------------------------------------------
     def assemble(self, pos, quat, dim, out, ld, *, chi=None, max_dist=0.0, layout=LAYOUT_CELL_MAJOR,

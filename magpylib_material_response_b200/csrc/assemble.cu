@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(SRC_TILE)
         const double lx = R.m[0] * dx + R.m[3] * dy + R.m[6] * dz;  // R^T d
         const double ly = R.m[1] * dx + R.m[4] * dy + R.m[7] * dz;
         const double lz = R.m[2] * dx + R.m[5] * dy + R.m[8] * dz;
-        cuboid_block<true>(lx, ly, lz, ha, hb, hc, N);
+        cuboid_block_auto<true>(lx, ly, lz, ha, hb, hc, N);
         rotate_block(R, N, blk);
       } else {
-        cuboid_block<true>(dx, dy, dz, ha, hb, hc, N);
+        cuboid_block_auto<true>(dx, dy, dz, ha, hb, hc, N);
         blk[0] = N.xx; blk[1] = N.xy; blk[2] = N.xz;
         blk[3] = N.xy; blk[4] = N.yy; blk[5] = N.yz;
         blk[6] = N.xz; blk[7] = N.yz; blk[8] = N.zz;
@@ -188,10 +188,10 @@ __global__ void __launch_bounds__(SRC_TILE)
         const double lx = R.m[0] * dx + R.m[3] * dy + R.m[6] * dz;
         const double ly = R.m[1] * dx + R.m[4] * dy + R.m[7] * dz;
         const double lz = R.m[2] * dx + R.m[5] * dy + R.m[8] * dz;
-        cuboid_block<true>(lx, ly, lz, 0.5 * d0, 0.5 * d1, 0.5 * d2, N);
+        cuboid_block_auto<true>(lx, ly, lz, 0.5 * d0, 0.5 * d1, 0.5 * d2, N);
         rotate_block(R, N, blk);
       } else {
-        cuboid_block<true>(dx, dy, dz, 0.5 * d0, 0.5 * d1, 0.5 * d2, N);
+        cuboid_block_auto<true>(dx, dy, dz, 0.5 * d0, 0.5 * d1, 0.5 * d2, N);
         blk[0] = N.xx; blk[1] = N.xy; blk[2] = N.xz;
         blk[3] = N.xy; blk[4] = N.yy; blk[5] = N.yz;
         blk[6] = N.xz; blk[7] = N.yz; blk[8] = N.zz;

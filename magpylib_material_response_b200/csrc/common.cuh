@@ -43,6 +43,7 @@ struct mmr_ctx {
   std::vector<cudaEvent_t> prof_pool;
   // side stream + events for look-ahead in the LU
   cudaStream_t side = nullptr;
+  bool lookahead = true;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -1,4 +1,6 @@
 // Context, error strings and workspace management for libmmr_b200.so.
+#include <cstdlib>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -107,6 +109,20 @@ extern "C" int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* u
   return 0;
 }
 
+extern "C" int64_t mmr_ctx_profile_records(mmr_ctx* ctx, int kind, double* ms_out, int64_t cap) {
+  if (!ctx || !ms_out) return 0;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  int64_t cnt = 0;
+  for (auto& r : ctx->prof) {
+    if (r.kind != kind || cnt >= cap) continue;
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms_out[cnt++] = t;
+  }
+  return cnt;
+}
+
 extern "C" int mmr_abi_version(void) { return MMR_ABI_VERSION; }
 extern "C" const char* mmr_last_error(void) { return g_err; }
 
@@ -133,7 +149,13 @@ extern "C" int mmr_ctx_create(int device, void* stream, mmr_ctx** out) {
     delete c;
     return -2;
   }
-  MMR_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    MMR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MMR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));  // panel look-ahead stream
+    const char* la = getenv("MMR_LU_LOOKAHEAD");
+    c->lookahead = !(la && la[0] == '0');
+  }
   for (int i = 0; i < 4; ++i) MMR_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
   *out = c;
   return 0;

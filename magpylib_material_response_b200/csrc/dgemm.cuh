@@ -41,6 +41,11 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Sign flip on the integer pipe (a DADD/DMUL negation would compete with the DMMAs for the FP64 pipe).
+__device__ __forceinline__ double flip_sign(double x) {
+  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 // ALIGNED16: A, B 16-byte aligned with even leading dimensions (cp.async 16 B); otherwise 8 B.
 // SUBTRACT : the LU form C <- C - A*B (alpha = -1, beta = 1).  The C tile is loaded straight into
 //            the accumulators (negated) BEFORE the main loop, so its DRAM latency overlaps the
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
-          if (gm < m && gn < n) acc[f][g][e] = -__ldcs(C + (int64_t)gn * ldc + gm);
+          if (gm < m && gn < n) acc[f][g][e] = flip_sign(__ldcs(C + (int64_t)gn * ldc + gm));
         }
     }
   }
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         if (gn < n) {
           double* cp = C + (int64_t)gn * ldc + gm;
           if (SUBTRACT) {
-            *cp = -acc[f][g][e];
+            *cp = flip_sign(acc[f][g][e]);
           } else {
             const double v = alpha * acc[f][g][e];
             *cp = (beta == 0.0) ? v : (v + beta * (*cp));

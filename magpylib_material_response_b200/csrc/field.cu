@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(OBS_TILE)
       const double ly = r.R[1] * dx + r.R[4] * dy + r.R[7] * dz;
       const double lz = r.R[2] * dx + r.R[5] * dy + r.R[8] * dz;
       SymBlock N;
-      cuboid_block<FIELD_H>(lx, ly, lz, r.ha, r.hb, r.hc, N);
+      cuboid_block_auto<FIELD_H>(lx, ly, lz, r.ha, r.hb, r.hc, N);
       const double fx = N.xx * r.jx + N.xy * r.jy + N.xz * r.jz;
       const double fy = N.xy * r.jx + N.yy * r.jy + N.yz * r.jz;
       const double fz = N.xz * r.jx + N.yz * r.jy + N.zz * r.jz;

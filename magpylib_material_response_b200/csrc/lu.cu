@@ -705,6 +705,33 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------
+// X = L^-1 for the unit-lower nb x nb diagonal block of a factored panel (column-major L, ldl).
+// One CTA, one thread per column of X (forward substitution); X is kept in shared memory and
+// written out as a dense nb x nb column-major matrix (upper part zero).  Runs on the look-ahead
+// stream, so the main stream's "TRSM" becomes a plain DMMA GEMM U12 = X * A12.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NB)
+    lu_trtri_kernel(const double* __restrict__ L, int64_t ldl, int nb, double* __restrict__ X) {
+  extern __shared__ __align__(16) double Xs[];  // Xs[c*(nb+1) + r]
+  const int c = threadIdx.x;
+  if (c < nb) {
+    double* x = Xs + c * (nb + 1);
+    for (int r = 0; r < c; ++r) x[r] = 0.0;
+    x[c] = 1.0;
+    for (int r = c + 1; r < nb; ++r) {
+      double acc = L[(int64_t)c * ldl + r];  // t = c term (x[c] = 1)
+      for (int t = c + 1; t < r; ++t) acc += L[(int64_t)t * ldl + r] * x[t];
+      x[r] = -acc;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    const int r = e % nb, cc = e / nb;
+    X[(int64_t)cc * nb + r] = Xs[cc * (nb + 1) + r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Triangular solves for Q x = b with Q^T = A = P L U:  U^T w = b,  L^T v = w,  x = P v.
 // Each "row" of U^T / L^T is a contiguous column of A, so the off-diagonal part is a
 // coalesced dot-product GEMV (one warp per column), the diagonal block a small serial solve.
@@ -804,7 +831,7 @@ extern "C" int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, doubl
 
 // Factor the panel columns [kb, kb+nb) rows [kb, N) of column-major A (local pointer/ld), pivots
 // into d_ipiv[kb..kb+nb) (global row indices).  Used by the single-GPU and distributed drivers.
-int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
+int mmr_lu_panel(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
                  int* d_info, void* d_scratch) {
   static int max_coop_ctas = -1;
   static size_t strip_smem_cap = 0;
@@ -854,7 +881,7 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
   for (int c0 = kb; c0 < kb + nb; c0 += W) {
     const int w = min(W, kb + nb - c0);
     const int m = N - c0;
-    const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, ctx->stream);
+    const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, strm);
     // cluster path: smallest power-of-two cluster that keeps >= 128 rows per CTA and fits smem
     int cs = 0;
     if (cluster_max >= 1) {
@@ -879,7 +906,7 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
       cfg.gridDim = dim3(csr);
       cfg.blockDim = dim3(RSTRIP_THREADS);
       cfg.dynamicSmemBytes = 0;
-      cfg.stream = ctx->stream;
+      cfg.stream = strm;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = csr;
@@ -897,7 +924,7 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
       cfg.gridDim = dim3(cs);
       cfg.blockDim = dim3(CSTRIP_THREADS);
       cfg.dynamicSmemBytes = (size_t)W * rows_per * sizeof(double);
-      cfg.stream = ctx->stream;
+      cfg.stream = strm;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = cs;
@@ -920,24 +947,24 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
       int w_arg = w, N_arg = N, c0_arg = c0;
       void* args[] = {&A, &ld, &N_arg, &c0_arg, &w_arg, &rows_per, &d_ipiv, &cand, &candrow, &diagrow, &d_info};
       MMR_CUDA(cudaLaunchCooperativeKernel((void*)lu_strip_kernel, dim3(G), dim3(STRIP_THREADS), args, smem,
-                                           ctx->stream));
+                                           strm));
     }
-    mmr_prof_end(ctx, pidx, (double)w, ctx->stream);
+    mmr_prof_end(ctx, pidx, (double)w, strm);
     ctx->launches++;
     const int ncol_other = nb - w;
     if (ncol_other > 0) {
-      lu_panel_swap_trsm_kernel<<<1, 128, 0, ctx->stream>>>(A, ld, c0, w, kb, kb + nb, d_ipiv);
+      lu_panel_swap_trsm_kernel<<<1, 128, 0, strm>>>(A, ld, c0, w, kb, kb + nb, d_ipiv);
       MMR_CHECK_LAUNCH(ctx);
     }
     const int nright = kb + nb - (c0 + w);
     const int mbelow = N - (c0 + w);
     if (nright > 0 && mbelow > 0) {
-      const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, ctx->stream);
-      int rc = mmr_dgemm_launch(ctx, ctx->stream, mbelow, nright, w, -1.0,
+      const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
+      int rc = mmr_dgemm_launch(ctx, strm, mbelow, nright, w, -1.0,
                                 A + (int64_t)c0 * ld + (c0 + w), ld,
                                 A + (int64_t)(c0 + w) * ld + c0, ld, 1.0,
                                 A + (int64_t)(c0 + w) * ld + (c0 + w), ld);
-      mmr_prof_end(ctx, pg, 2.0 * mbelow * nright * w, ctx->stream);
+      mmr_prof_end(ctx, pg, 2.0 * mbelow * nright * w, strm);
       if (rc) return rc;
     }
   }
@@ -946,17 +973,17 @@ int mmr_lu_panel(mmr_ctx* ctx, double* A, int64_t ld, int N, int kb, int nb, int
 
 size_t mmr_lu_panel_scratch_bytes() { return 2 * 256 * sizeof(Cand) + (2 * 256 * W + 2 * W) * sizeof(double); }
 
-int mmr_lu_laswp(mmr_ctx* ctx, double* A, int64_t ld, int k0, int k1, int col_begin, int col_end,
+int mmr_lu_laswp(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int k0, int k1, int col_begin, int col_end,
                  const int* d_ipiv) {
   if (col_end <= col_begin || k1 <= k0) return 0;
   const int threads = 128;
   lu_laswp_kernel<<<(unsigned)ceil_div64(col_end - col_begin, threads), threads, (k1 - k0) * sizeof(int),
-                    ctx->stream>>>(A, ld, k0, k1, col_begin, col_end, d_ipiv);
+                    strm>>>(A, ld, k0, k1, col_begin, col_end, d_ipiv);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
 
-int mmr_lu_trsm(mmr_ctx* ctx, const double* L, int64_t ldl, int nb, double* B, int64_t ldb, int ncols) {
+int mmr_lu_trsm(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, int nb, double* B, int64_t ldb, int ncols) {
   if (ncols <= 0 || nb <= 0) return 0;
   const size_t smem = ((size_t)TRSM_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
   static size_t cap = 0;
@@ -964,7 +991,19 @@ int mmr_lu_trsm(mmr_ctx* ctx, const double* L, int64_t ldl, int nb, double* B, i
     MMR_CUDA(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cap = smem;
   }
-  lu_trsm_kernel<<<(unsigned)ceil_div64(ncols, TRSM_COLS), 256, smem, ctx->stream>>>(L, ldl, nb, B, ldb, ncols);
+  lu_trsm_kernel<<<(unsigned)ceil_div64(ncols, TRSM_COLS), 256, smem, strm>>>(L, ldl, nb, B, ldb, ncols);
+  MMR_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int mmr_lu_trtri(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, int nb, double* X) {
+  const size_t smem = (size_t)nb * (nb + 1) * sizeof(double);
+  static size_t cap = 0;
+  if (smem > cap) {
+    MMR_CUDA(cudaFuncSetAttribute(lu_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cap = smem;
+  }
+  lu_trtri_kernel<<<1, NB, smem, strm>>>(L, ldl, nb, X);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -979,41 +1018,81 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   MMR_ARG(d_Q && d_ipiv, "NULL matrix/pivot pointer");
   DeviceGuard g(ctx->device);
   const int N = (int)N64;
-  int rc = mmr_ws_reserve(ctx, 256 + mmr_lu_panel_scratch_bytes());
+  const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 2 * sizeof(double) * NB * NB);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 256);
   if (rc) return rc;
   int* d_info = (int*)ctx->ws;
   void* scratch = (char*)ctx->ws + 256;
+  double* Linv[2] = {(double*)((char*)ctx->ws + 256 + scratch_bytes),
+                     (double*)((char*)ctx->ws + 256 + scratch_bytes) + NB * NB};
   MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
   double* A = d_Q;
+  cudaStream_t main_s = ctx->stream;
+  cudaStream_t side_s = ctx->side;
+  // trailing update of the column range [cb, ce) by panel kb (swaps, U12 = L11^-1 A12, A22 -= L21 U12)
+  auto update_cols = [&](int kb, int nb, int cb, int ce) -> int {
+    if (ce <= cb) return 0;
+    int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, main_s);
+    int r = mmr_lu_laswp(ctx, main_s, A, ld, kb, kb + nb, cb, ce, d_ipiv);
+    if (r) return r;
+    mmr_prof_end(ctx, ps, 32.0 * nb * (double)(ce - cb), main_s);
+    // U12 = L11^-1 A12 as an in-place DMMA GEMM (one m-tile: each CTA reads its whole B tile
+    // into shared memory before it stores, and no other CTA touches those columns)
+    ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, main_s);
+    r = mmr_dgemm_launch(ctx, main_s, nb, ce - cb, nb, 1.0, Linv[(kb / NB) & 1], nb, A + (int64_t)cb * ld + kb, ld,
+                         0.0, A + (int64_t)cb * ld + kb, ld);
+    if (r) return r;
+    mmr_prof_end(ctx, ps, 2.0 * nb * nb * (ce - cb), main_s);
+    const int mrows = N - (kb + nb);
+    ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, main_s);
+    r = mmr_dgemm_launch(ctx, main_s, mrows, ce - cb, nb, -1.0, A + (int64_t)kb * ld + (kb + nb), ld,
+                         A + (int64_t)cb * ld + kb, ld, 1.0, A + (int64_t)cb * ld + (kb + nb), ld);
+    if (r) return r;
+    mmr_prof_end(ctx, ps, 2.0 * mrows * (double)(ce - cb) * nb, main_s);
+    return 0;
+  };
+  // Look-ahead (depth 1): as soon as the columns of panel k+1 have received the update of panel
+  // k, panel k+1 is factored on the high-priority side stream while the main stream applies the
+  // rest of update k.  The two touch disjoint column ranges.
+  const bool lookahead = ctx->lookahead;
+  rc = mmr_lu_panel(ctx, main_s, A, ld, N, 0, min(NB, N), d_ipiv, d_info, scratch);
+  if (rc) return rc;
+  rc = mmr_lu_trtri(ctx, main_s, A, ld, min(NB, N), Linv[0]);
+  if (rc) return rc;
   for (int kb = 0; kb < N; kb += NB) {
     const int nb = min(NB, N - kb);
-    rc = mmr_lu_panel(ctx, A, ld, N, kb, nb, d_ipiv, d_info, scratch);
-    if (rc) return rc;
-    // swaps on the columns left and right of the panel
-    const int ntrail = N - (kb + nb);
-    int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, ctx->stream);
-    rc = mmr_lu_laswp(ctx, A, ld, kb, kb + nb, 0, kb, d_ipiv);
-    if (rc) return rc;
-    if (ntrail > 0) {
-      rc = mmr_lu_laswp(ctx, A, ld, kb, kb + nb, kb + nb, N, d_ipiv);
+    const int next = kb + nb;
+    // left swaps of panel kb (columns already factored)
+    {
+      const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, main_s);
+      rc = mmr_lu_laswp(ctx, main_s, A, ld, kb, kb + nb, 0, kb, d_ipiv);
       if (rc) return rc;
+      mmr_prof_end(ctx, ps, 32.0 * nb * (double)kb, main_s);
     }
-    mmr_prof_end(ctx, ps, 32.0 * nb * (double)(N - nb), ctx->stream);
-    if (ntrail > 0) {
-      // U12 = L11^-1 A12
-      ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, ctx->stream);
-      rc = mmr_lu_trsm(ctx, A + (int64_t)kb * ld + kb, ld, nb, A + (int64_t)(kb + nb) * ld + kb, ld, ntrail);
+    if (next >= N) break;
+    const int nb2 = min(NB, N - next);
+    rc = update_cols(kb, nb, next, next + nb2);
+    if (rc) return rc;
+    if (lookahead) {
+      MMR_CUDA(cudaEventRecord(ctx->ev[0], main_s));
+      MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
+      rc = mmr_lu_panel(ctx, side_s, A, ld, N, next, nb2, d_ipiv, d_info, scratch);
       if (rc) return rc;
-      mmr_prof_end(ctx, ps, (double)nb * nb * ntrail, ctx->stream);
-      // A22 -= L21 U12
-      ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, ctx->stream);
-      rc = mmr_dgemm_launch(ctx, ctx->stream, ntrail, ntrail, nb, -1.0, A + (int64_t)kb * ld + (kb + nb), ld,
-                            A + (int64_t)(kb + nb) * ld + kb, ld, 1.0,
-                            A + (int64_t)(kb + nb) * ld + (kb + nb), ld);
+      rc = mmr_lu_trtri(ctx, side_s, A + (int64_t)next * ld + next, ld, nb2, Linv[(next / NB) & 1]);
       if (rc) return rc;
-      mmr_prof_end(ctx, ps, 2.0 * ntrail * (double)ntrail * nb, ctx->stream);
+      MMR_CUDA(cudaEventRecord(ctx->ev[1], side_s));
+      rc = update_cols(kb, nb, next + nb2, N);
+      if (rc) return rc;
+      MMR_CUDA(cudaStreamWaitEvent(main_s, ctx->ev[1], 0));
+    } else {
+      rc = update_cols(kb, nb, next + nb2, N);
+      if (rc) return rc;
+      rc = mmr_lu_panel(ctx, main_s, A, ld, N, next, nb2, d_ipiv, d_info, scratch);
+      if (rc) return rc;
+      rc = mmr_lu_trtri(ctx, main_s, A + (int64_t)next * ld + next, ld, nb2, Linv[(next / NB) & 1]);
+      if (rc) return rc;
     }
   }
   MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -173,7 +173,12 @@ def test_max_dist_masks_exactly_the_reference_pairs(ctx, max_dist):
     n = len(pos)
     ref = oref.tensor_to_matrix(oref.demag_tensor_ref(pos, quat, dim, max_dist=max_dist))
     got = cell_major_to_reference(assemble_numpy(ctx, pos, quat, dim, max_dist=max_dist), n)
-    assert np.array_equal(got == 0, ref == 0)
+    # masked pairs (flat index i*n+j, demag.py:245-249) are EXACTLY zero, kept pairs are evaluated
+    keep = oref.filter_distance_mask(pos, dim, max_dist).reshape(n, n)  # [i source, j observer]
+    blocks = got.reshape(3, n, 3, n).transpose(3, 1, 0, 2)  # [i, j, l, k]
+    assert not blocks[~keep].any()
+    if keep.any():
+        assert np.abs(blocks[keep]).max(axis=(1, 2)).min() > 0
     assert_T_close(got, ref)
 
 

@@ -17,10 +17,11 @@ for r in range(reps):
     ctx.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); info = ctx.lu_factor(Q, ld, ipiv); e1.record(); ctx.lu_solve(Q, ld, ipiv, x); torch.cuda.synchronize()
-    prof = ctx.profile(); ctx.set_profiling(False)
+    prof = ctx.profile(); recs = ctx.profile_records('panel'); ctx.set_profiling(False)
     t = e0.elapsed_time(e1)
     if best is None or t < best[0]: best = (t, prof)
 y = torch.empty_like(b); ctx.matvec(Q0, ld, x, y)
 res = float(torch.linalg.norm(y - b) / torch.linalg.norm(b))
+import numpy as _np; _r=_np.array(recs); print("panel records: n", len(_r), "sum", _r.sum(), "max", _r.max(), "argmax", int(_r.argmax()), "n>1ms", int((_r>1).sum()), "idx>1ms", _np.nonzero(_r>1)[0][:20].tolist(), file=sys.stderr)
 print(json.dumps({"N": N, "factor_ms": best[0], "tflops": (2 / 3) * N**3 / (best[0] * 1e-3) / 1e12, "info": info, "relres": res,
                   "stages_ms": {k: round(v[0], 2) for k, v in best[1].items() if v[2]}}))
