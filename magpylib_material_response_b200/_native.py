@@ -314,13 +314,13 @@ class Context:
         torch.distributed (the process group is plumbing only)."""
         import torch.distributed as dist
 
+        from .distributed import broadcast_bytes
+
         world, rank = dist.get_world_size(), dist.get_rank()
         idbuf = (ctypes.c_char * 128)()
         if rank == 0:
             _check(self.lib, self.lib.mmr_nccl_unique_id(ctypes.cast(idbuf, ctypes.c_void_p)))
-        payload = [bytes(idbuf)]
-        dist.broadcast_object_list(payload, src=0)
-        idbuf = ctypes.create_string_buffer(payload[0], 128)
+        idbuf = ctypes.create_string_buffer(broadcast_bytes(bytes(idbuf), src=0), 128)
         _check(self.lib, self.lib.mmr_comm_init(self.handle, ctypes.cast(idbuf, ctypes.c_void_p), world, rank))
         self.nranks, self.rank = world, rank
 

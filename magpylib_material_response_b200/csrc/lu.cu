@@ -1181,3 +1181,190 @@ extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64
   }
   return 0;
 }
+
+// =======================================================================================
+// Multi-GPU: 1-D block-cyclic distributed LU + solve (one process per GPU, NCCL).
+//
+// Global column panel s of A = Q^T (= row block s of Q: the rows of tgt_block cells, width
+// nbw = 3*tgt_block <= 128) lives on rank s % R at local column offset (s / R) * nbw.  The pivot
+// search of a panel is local to its owner; the factored panel, its pivots and L11^-1 are
+// broadcast; every rank then swaps and updates its own trailing columns with the same DMMA GEMM
+// as the single-GPU path.  The triangular solves walk the panels in order with one nbw-double
+// broadcast per panel.
+// =======================================================================================
+#include "comm.h"
+
+namespace {
+
+// b[c0 + c] -= sum_{r in [r0, r1)} Acol[(c0 + c)*ld + r] * x[r]; one CTA per column
+__global__ void __launch_bounds__(256)
+    lu_gemv_t_block_kernel(const double* __restrict__ Acol, int64_t ld, int r0, int r1, int c0,
+                           const double* x, double* b) {
+  __shared__ double s_part[8];
+  const int c = c0 + blockIdx.x;
+  const double* a = Acol + (int64_t)c * ld;
+  double acc = 0.0;
+  for (int r = r0 + threadIdx.x; r < r1; r += 256) acc += a[r] * x[r];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += s_part[q];
+    b[c] -= t;
+  }
+}
+
+}  // namespace
+
+extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local, int64_t tgt_block,
+                                 double* d_Qlocal, int64_t ld, double* d_b, int* info_out) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(N64 >= 0 && N64 < (1LL << 31) && N64 % 3 == 0, "N out of range / not a multiple of 3");
+  MMR_ARG(ld >= N64 && tgt_block >= 1 && nrows_local >= 0, "bad sizes");
+  MMR_ARG(3 * tgt_block <= NB, "distributed LU needs 3*tgt_block <= 128");
+  MMR_ARG(ctx->nranks == 1 || ctx->nccl_comm != nullptr, "communicator not initialised");
+  if (info_out) *info_out = 0;
+  if (N64 == 0) return 0;
+  MMR_ARG(d_b && (d_Qlocal || nrows_local == 0), "NULL pointer");
+  DeviceGuard g(ctx->device);
+  const int N = (int)N64;
+  const int R = ctx->nranks, me = ctx->rank;
+  const int nbw = (int)(3 * tgt_block);
+  const int S = (int)ceil_div64(N, nbw);
+  {
+    int64_t mine = 0;
+    for (int s = me; s < S; s += R) mine += min(nbw, N - s * nbw);
+    MMR_ARG(mine == nrows_local, "nrows_local does not match the block-cyclic ownership of this rank");
+  }
+  const int ncols_local = (int)nrows_local;
+  cudaStream_t st = ctx->stream;
+
+  const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
+  const size_t linv_bytes = sizeof(double) * NB * NB;
+  const size_t ipiv_bytes = ((sizeof(int) * (size_t)N + 255) / 256) * 256;
+  const size_t p_bytes = sizeof(double) * (size_t)N * nbw;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + linv_bytes + ipiv_bytes + p_bytes + sizeof(double) * (size_t)N + 512);
+  if (rc) return rc;
+  rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
+  if (rc) return rc;
+  char* base = (char*)ctx->ws;
+  int* d_info = (int*)base;
+  void* scratch = base + 256;
+  double* Linv = (double*)(base + 256 + scratch_bytes);
+  int* d_ipiv = (int*)(base + 256 + scratch_bytes + linv_bytes);
+  double* P = (double*)(base + 256 + scratch_bytes + linv_bytes + ipiv_bytes);
+  double* d_tmp = P + (size_t)N * nbw;
+  MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+  double* Al = d_Qlocal;
+
+  for (int s = 0; s < S; ++s) {
+    const int kb = s * nbw;
+    const int nb = min(nbw, N - kb);
+    const int m = N - kb;
+    const int owner = s % R;
+    if (me == owner) {
+      double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;  // global column kb -> my local column
+      rc = mmr_lu_panel(ctx, st, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
+      if (rc) return rc;
+      rc = mmr_lu_trtri(ctx, st, Ash + (int64_t)kb * ld + kb, ld, nb, Linv);
+      if (rc) return rc;
+      MMR_CUDA(cudaMemcpy2DAsync(P, sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
+                                 sizeof(double) * m, nb, cudaMemcpyDeviceToDevice, st));
+    }
+    if (R > 1) {
+      rc = mmr_comm_bcast_bytes(ctx, P, sizeof(double) * (size_t)m * nb, owner, st);
+      if (rc) return rc;
+      rc = mmr_comm_bcast_bytes(ctx, Linv, sizeof(double) * (size_t)nb * nb, owner, st);
+      if (rc) return rc;
+      rc = mmr_comm_bcast_bytes(ctx, d_ipiv + kb, sizeof(int) * (size_t)nb, owner, st);
+      if (rc) return rc;
+    }
+    // my already-factored panels (global index < s): row swaps only
+    const int nleft = (s > me) ? ((s - 1 - me) / R + 1) : 0;
+    rc = mmr_lu_laswp(ctx, st, Al, ld, kb, kb + nb, 0, nleft * nbw, d_ipiv);
+    if (rc) return rc;
+    // my trailing panels (global index > s)
+    const int first_trail = (s >= me) ? ((s - me) / R + 1) : 0;
+    const int ct0 = first_trail * nbw, ct1 = ncols_local;
+    if (ct1 > ct0) {
+      rc = mmr_lu_laswp(ctx, st, Al, ld, kb, kb + nb, ct0, ct1, d_ipiv);
+      if (rc) return rc;
+      int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
+      rc = mmr_dgemm_launch(ctx, st, nb, ct1 - ct0, nb, 1.0, Linv, nb, Al + (int64_t)ct0 * ld + kb, ld, 0.0,
+                            Al + (int64_t)ct0 * ld + kb, ld);
+      if (rc) return rc;
+      mmr_prof_end(ctx, ps, 2.0 * nb * nb * (ct1 - ct0), st);
+      if (m > nb) {
+        ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);
+        rc = mmr_dgemm_launch(ctx, st, m - nb, ct1 - ct0, nb, -1.0, P + nb, m, Al + (int64_t)ct0 * ld + kb, ld, 1.0,
+                              Al + (int64_t)ct0 * ld + kb + nb, ld);
+        if (rc) return rc;
+        mmr_prof_end(ctx, ps, 2.0 * (m - nb) * (double)(ct1 - ct0) * nb, st);
+      }
+    }
+  }
+
+  // ---- triangular solves, panel by panel --------------------------------------------------
+  const size_t diag_smem = (size_t)SB * (SB + 1) * sizeof(double);
+  MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
+  MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
+  for (int s = 0; s < S; ++s) {  // U^T w = b
+    const int kb = s * nbw, nb = min(nbw, N - kb), owner = s % R;
+    if (me == owner) {
+      const double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;
+      if (kb > 0) {
+        lu_gemv_t_block_kernel<<<nb, 256, 0, st>>>(Ash, ld, 0, kb, kb, d_b, d_b);
+        MMR_CHECK_LAUNCH(ctx);
+      }
+      lu_diag_solve_kernel<true><<<1, SB, diag_smem, st>>>(Ash, ld, kb, kb + nb, d_b);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+    if (R > 1) {
+      rc = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * nb, owner, st);
+      if (rc) return rc;
+    }
+  }
+  for (int s = S - 1; s >= 0; --s) {  // L^T v = w
+    const int kb = s * nbw, nb = min(nbw, N - kb), owner = s % R;
+    if (me == owner) {
+      const double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;
+      if (kb + nb < N) {
+        lu_gemv_t_block_kernel<<<nb, 256, 0, st>>>(Ash, ld, kb + nb, N, kb, d_b, d_b);
+        MMR_CHECK_LAUNCH(ctx);
+      }
+      lu_diag_solve_kernel<false><<<1, SB, diag_smem, st>>>(Ash, ld, kb, kb + nb, d_b);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+    if (R > 1) {
+      rc = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * nb, owner, st);
+      if (rc) return rc;
+    }
+  }
+  // ---- x = P v (pivots are replicated) ------------------------------------------------------
+  int* h_ipiv = (int*)ctx->hpin;
+  int* h_perm = h_ipiv + N;
+  MMR_CUDA(cudaMemcpyAsync(h_ipiv, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+  MMR_CUDA(cudaMemcpyAsync(h_perm, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MMR_CUDA(cudaStreamSynchronize(st));
+  const int info = h_perm[0];
+  for (int i = 0; i < N; ++i) h_perm[i] = i;
+  for (int i = N - 1; i >= 0; --i) {
+    const int p = h_ipiv[i];
+    if (p != i) {
+      const int t = h_perm[i];
+      h_perm[i] = h_perm[p];
+      h_perm[p] = t;
+    }
+  }
+  int* d_perm = d_ipiv;  // pivots no longer needed on the device
+  MMR_CUDA(cudaMemcpyAsync(d_perm, h_perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+  MMR_CUDA(cudaMemcpyAsync(d_tmp, d_b, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+  lu_gather_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(d_tmp, d_perm, N, d_b);
+  MMR_CHECK_LAUNCH(ctx);
+  MMR_CUDA(cudaStreamSynchronize(st));
+  if (info_out) *info_out = info;  // only the owner of a zero pivot sees it; callers reduce over ranks
+  return 0;
+}

@@ -1,12 +1,265 @@
-// pairs_matching assembly (demag.py:280-321) -- unique-pair table on device.
+// pairs_matching assembly (replaces match_pairs + the gather of demag.py:280-321, :198).
+//
+// The reference builds an n^2 x 14 key matrix on the host and runs np.unique(axis=0) over it
+// (81.6 GB at n = 27000).  Here the unique pairs are found with a lock-free open-addressing table
+// on the device, keyed like the reference:  rint((p_j - p_i + 1e-9) * 1e8) per axis (= its
+// "(x + 1e-9).round(8)") plus the source cell's class id (rounded orientation + dimension, computed
+// on the host over n rows).  A slot stores one member pair (enough to
+// recompute the key for comparison) and, via atomicMin, the smallest flat index i*n+j of the class --
+// the same representative np.unique(return_index=True) picks.  Then
+//   1. insert all n^2 pairs            (L2-resident table, one atomic per new class)
+//   2. evaluate one 3x3 block per class (the only transcendental work)
+//   3. scatter blocks to all pairs      (72 B written per pair: HBM-write bound)
 #include "cuboid.cuh"
+
+namespace {
+
+constexpr int SRC_TILE = 128;
+constexpr int TGT_TILE = 32;
+typedef unsigned long long u64;
+
+struct MatchParams {
+  int64_t n;
+  const double* pos;
+  const double* quat;
+  const double* dim;
+  const int32_t* cls;
+  const double* chi;
+  double* out;
+  int64_t ld;
+  u64* tab;      // member pair index + 1, 0 = empty
+  u64* minrep;   // smallest pair index of the class
+  double* blocks;  // 9 doubles per slot
+  u64 mask;      // capacity - 1 (capacity is a power of two)
+  int* status;   // [0] = number of classes, [1] = overflow flag
+  int rotated;
+};
+
+struct PairKey {
+  long long kx, ky, kz;
+  int cls;
+};
+
+__device__ __forceinline__ PairKey make_key(const MatchParams& p, int64_t i, int64_t j) {
+  PairKey k;
+  // (p_j - p_i + 1e-9).round(8): numpy rounds via rint(x * 1e8) / 1e8
+  k.kx = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 0], p.pos[3 * i + 0]), 1e-9), 1e8));
+  k.ky = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 1], p.pos[3 * i + 1]), 1e-9), 1e8));
+  k.kz = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 2], p.pos[3 * i + 2]), 1e-9), 1e8));
+  k.cls = p.cls[i];
+  return k;
+}
+
+__device__ __forceinline__ bool same_key(const PairKey& a, const PairKey& b) {
+  return a.kx == b.kx && a.ky == b.ky && a.kz == b.kz && a.cls == b.cls;
+}
+
+__device__ __forceinline__ u64 hash_key(const PairKey& k) {
+  u64 h = (u64)k.kx * 0x9E3779B97F4A7C15ull;
+  h ^= (u64)k.ky + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  h *= 0xC2B2AE3D27D4EB4Full;
+  h ^= (u64)k.kz + 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+  h *= 0x9E3779B97F4A7C15ull;
+  h ^= (u64)(unsigned)k.cls + (h << 6) + (h >> 2);
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h;
+}
+
+// slot of the class of pair (i,j); inserts if INSERT.  Returns ~0 on overflow.
+template <bool INSERT>
+__device__ __forceinline__ u64 find_slot(const MatchParams& p, int64_t i, int64_t j) {
+  const PairKey key = make_key(p, i, j);
+  const u64 me = (u64)(i * p.n + j);
+  u64 h = hash_key(key) & p.mask;
+  for (u64 probes = 0; probes <= p.mask; ++probes) {
+    u64 cur = p.tab[h];
+    if (cur == 0) {
+      if (!INSERT) return ~0ull;
+      const u64 old = atomicCAS(&p.tab[h], 0ull, me + 1);
+      if (old == 0) {
+        atomicAdd(&p.status[0], 1);
+        atomicMin(&p.minrep[h], me);
+        return h;
+      }
+      cur = old;
+    }
+    const u64 member = cur - 1;
+    const PairKey other = make_key(p, (int64_t)(member / (u64)p.n), (int64_t)(member % (u64)p.n));
+    if (same_key(key, other)) {
+      if (INSERT && me < p.minrep[h]) atomicMin(&p.minrep[h], me);
+      return h;
+    }
+    h = (h + 1) & p.mask;
+  }
+  return ~0ull;
+}
+
+__global__ void __launch_bounds__(256) match_insert_kernel(const MatchParams p) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // observer (fast index)
+  if (j >= p.n) return;
+  for (int64_t i = blockIdx.y; i < p.n; i += gridDim.y) {  // source
+    if (p.status[1]) return;
+    if (find_slot<true>(p, i, j) == ~0ull) atomicExch(&p.status[1], 1);
+    // load factor guard: stop early once the table is more than half full
+    if (threadIdx.x == 0 && (u64)p.status[0] * 2 > p.mask + 1) atomicExch(&p.status[1], 1);
+  }
+}
+
+__global__ void __launch_bounds__(128) match_eval_kernel(const MatchParams p) {
+  const u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h > p.mask) return;
+  if (p.tab[h] == 0) return;
+  const u64 rep = p.minrep[h];
+  const int64_t i = (int64_t)(rep / (u64)p.n), j = (int64_t)(rep % (u64)p.n);
+  const double dx = p.pos[3 * j + 0] - p.pos[3 * i + 0];
+  const double dy = p.pos[3 * j + 1] - p.pos[3 * i + 1];
+  const double dz = p.pos[3 * j + 2] - p.pos[3 * i + 2];
+  const double ha = 0.5 * p.dim[3 * i + 0], hb = 0.5 * p.dim[3 * i + 1], hc = 0.5 * p.dim[3 * i + 2];
+  double blk[9];
+  SymBlock N;
+  if (p.rotated) {
+    Rot3 R;
+    quat_to_rot(p.quat + 4 * i, R);
+    const double lx = R.m[0] * dx + R.m[3] * dy + R.m[6] * dz;
+    const double ly = R.m[1] * dx + R.m[4] * dy + R.m[7] * dz;
+    const double lz = R.m[2] * dx + R.m[5] * dy + R.m[8] * dz;
+    cuboid_block_auto<true>(lx, ly, lz, ha, hb, hc, N);
+    rotate_block(R, N, blk);
+  } else {
+    cuboid_block_auto<true>(dx, dy, dz, ha, hb, hc, N);
+    blk[0] = N.xx; blk[1] = N.xy; blk[2] = N.xz;
+    blk[3] = N.xy; blk[4] = N.yy; blk[5] = N.yz;
+    blk[6] = N.xz; blk[7] = N.yz; blk[8] = N.zz;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) p.blocks[h * 9 + q] = blk[q];
+}
+
+template <bool FUSE_Q>
+__global__ void __launch_bounds__(SRC_TILE) match_scatter_kernel(const MatchParams p) {
+  __shared__ double s_tchi[TGT_TILE][3];
+  __shared__ double s_stage[SRC_TILE / 32][3][96];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t0 = (int64_t)blockIdx.y * TGT_TILE;
+  const int ntgt = (int)min((int64_t)TGT_TILE, p.n - t0);
+  if (FUSE_Q && tid < ntgt) {
+    s_tchi[tid][0] = p.chi[3 * (t0 + tid) + 0];
+    s_tchi[tid][1] = p.chi[3 * (t0 + tid) + 1];
+    s_tchi[tid][2] = p.chi[3 * (t0 + tid) + 2];
+  }
+  const int64_t i_warp0 = (int64_t)blockIdx.x * SRC_TILE + warp * 32;
+  const int64_t i = i_warp0 + lane;
+  const int64_t ic = i < p.n ? i : p.n - 1;
+  __syncthreads();
+  const int64_t ncols_warp = min((int64_t)96, 3 * (p.n - i_warp0));
+  for (int tt = 0; tt < ntgt; ++tt) {
+    const int64_t j = t0 + tt;
+    const u64 h = find_slot<false>(p, ic, j);
+    double blk[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) blk[q] = (h != ~0ull) ? p.blocks[h * 9 + q] : 0.0;
+    if (FUSE_Q) {
+      const bool diag = (j == i);
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double chi = s_tchi[tt][l];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double v = -(chi * blk[3 * l + k]);
+          blk[3 * l + k] = (diag && l == k) ? (1.0 + v) : v;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s_stage[warp][l][3 * lane + k] = blk[3 * l + k];
+    __syncwarp();
+    double* row_base = p.out + (3 * j) * p.ld + 3 * i_warp0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int c = q * 32 + lane;
+        if (c < ncols_warp) row_base[l * p.ld + c] = s_stage[warp][l][c];
+      }
+  }
+}
+
+}  // namespace
+
+int mmr_detect_rotated(mmr_ctx* ctx, int64_t n, const double* d_quat, int* rotated_out);
 
 extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
                                     const double* d_dim, const int32_t* d_cls, const double* d_chi,
                                     double* d_out, int64_t ld, int64_t table_cap_slots,
                                     int64_t* n_unique_out) {
-  (void)ctx; (void)n; (void)d_pos; (void)d_quat; (void)d_dim; (void)d_cls; (void)d_chi; (void)d_out; (void)ld;
-  (void)table_cap_slots; (void)n_unique_out;
-  mmr_set_error("mmr_assemble_matched: not implemented yet");
-  return -7;
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(n >= 0, "negative n");
+  if (n_unique_out) *n_unique_out = 0;
+  if (n == 0) return 0;
+  MMR_ARG(d_pos && d_quat && d_dim && d_cls && d_out, "NULL pointer");
+  MMR_ARG(ld >= 3 * n, "ld must be >= 3*n");
+  MMR_ARG(table_cap_slots >= 2, "table_cap_slots too small");
+  DeviceGuard g(ctx->device);
+  int rc = mmr_ws_reserve(ctx, 256);
+  if (rc) return rc;
+  rc = mmr_hpin_reserve(ctx, 256);
+  if (rc) return rc;
+  int rotated = 0;
+  rc = mmr_detect_rotated(ctx, n, d_quat, &rotated);
+  if (rc) return rc;
+
+  // capacity: power of two, grown on overflow up to table_cap_slots
+  u64 cap = 1ull << 16;
+  while (cap < 4096ull * 16 && cap < (u64)table_cap_slots) cap <<= 1;
+  const u64 npairs = (u64)n * (u64)n;
+  for (;;) {
+    while (cap > (u64)table_cap_slots) cap >>= 1;
+    const size_t bytes = 256 + cap * (sizeof(u64) * 2 + sizeof(double) * 9);
+    rc = mmr_ws2_reserve(ctx, bytes);
+    if (rc) return rc;
+    char* base = (char*)ctx->ws2;
+    MatchParams p;
+    p.n = n; p.pos = d_pos; p.quat = d_quat; p.dim = d_dim; p.cls = d_cls; p.chi = d_chi;
+    p.out = d_out; p.ld = ld;
+    p.status = (int*)base;
+    p.tab = (u64*)(base + 256);
+    p.minrep = p.tab + cap;
+    p.blocks = (double*)(p.minrep + cap);
+    p.mask = cap - 1;
+    p.rotated = rotated;
+    MMR_CUDA(cudaMemsetAsync(p.status, 0, 256, ctx->stream));
+    MMR_CUDA(cudaMemsetAsync(p.tab, 0, sizeof(u64) * cap, ctx->stream));
+    MMR_CUDA(cudaMemsetAsync(p.minrep, 0xff, sizeof(u64) * cap, ctx->stream));
+    dim3 gi((unsigned)ceil_div64(n, 256), (unsigned)(n < 32768 ? n : 32768));
+    match_insert_kernel<<<gi, 256, 0, ctx->stream>>>(p);
+    MMR_CHECK_LAUNCH(ctx);
+    MMR_CUDA(cudaMemcpyAsync(ctx->hpin, p.status, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int nclasses = ((int*)ctx->hpin)[0];
+    const int overflow = ((int*)ctx->hpin)[1];
+    if (overflow) {
+      if (cap * 2 > (u64)table_cap_slots || cap >= 2 * npairs) {
+        mmr_set_error("pairs_matching: more than %llu unique pairs (table cap %lld slots)",
+                      (unsigned long long)(cap / 2), (long long)table_cap_slots);
+        return -3;
+      }
+      cap <<= 2;
+      continue;
+    }
+    match_eval_kernel<<<(unsigned)ceil_div64((int64_t)cap, 128), 128, 0, ctx->stream>>>(p);
+    MMR_CHECK_LAUNCH(ctx);
+    dim3 gs((unsigned)ceil_div64(n, SRC_TILE), (unsigned)ceil_div64(n, TGT_TILE));
+    const int pidx = mmr_prof_begin(ctx, MMR_PROF_ASSEMBLE, ctx->stream);
+    if (d_chi) match_scatter_kernel<true><<<gs, SRC_TILE, 0, ctx->stream>>>(p);
+    else match_scatter_kernel<false><<<gs, SRC_TILE, 0, ctx->stream>>>(p);
+    mmr_prof_end(ctx, pidx, (double)n * (double)n, ctx->stream);
+    MMR_CHECK_LAUNCH(ctx);
+    if (n_unique_out) *n_unique_out = nclasses;
+    return 0;
+  }
 }

@@ -313,12 +313,44 @@ def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching
                        split=1, solver="lu", tol=1e-12, device=None, min_log_time=None):
     """Host arrays in, host array out: assemble Q = I - chi*N on the device, solve
     Q x = J0 + chi*H_ext (demag.py:444-470).  All (n,3) arrays, GLOBAL frame.  Returns (x, info)."""
+    from . import distributed as mdist
+
     ctx = _native.default_context(device)
     torch = ctx.torch
     n = len(pos)
     N = 3 * n
     info = {}
     rhs = (np.asarray(pol_global, dtype=float) + np.asarray(chi, dtype=float) * np.asarray(H_ext, dtype=float)).reshape(N)
+    if mdist.ensure_comm(ctx) > 1:
+        # one process per GPU: this rank assembles and owns a block-cyclic set of target-row blocks
+        # (no exchange during assembly); every rank returns the full solution.
+        tgt_block = mdist.DEFAULT_TGT_BLOCK
+        n_local = len(mdist.owned_cells(n, tgt_block, ctx.nranks, ctx.rank))
+        ld = _padded_ld(N)
+        d_pos, d_quat, d_dim = ctx.to_device(pos), ctx.to_device(quat), ctx.to_device(dim)
+        d_chi = ctx.to_device(np.asarray(chi, dtype=float).reshape(N))
+        Q = ctx.empty(3 * n_local, ld)
+        with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):
+            ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, max_dist=max_dist, n_tgt_local=n_local,
+                         tgt_block=tgt_block, tgt_nparts=ctx.nranks, tgt_part=ctx.rank)
+        with timelog("Solving of linear system", min_log_time=min_log_time):
+            d_x = ctx.to_device(rhs)
+            if solver == "lu":
+                lu_info = ctx.lu_solve_dist(N, 3 * n_local, tgt_block, Q, ld, d_x)
+                flag = torch.tensor([lu_info], device=ctx.device)
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                if int(flag.item()) != 0:
+                    msg = f"Singular matrix (zero pivot at elimination step {int(flag.item())})"
+                    raise np.linalg.LinAlgError(msg)
+            else:
+                d_b = d_x
+                d_x = torch.zeros_like(d_b)
+                iters, relres = ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_b, d_x, tol=tol,
+                                               restart=min(300, N), maxit=max(1000, 2 * N))
+                info["gmres_iters"], info["gmres_relres"] = iters, relres
+            x = d_x.cpu().numpy().reshape(n, 3)
+        info["n_gpus"] = ctx.nranks
+        return x, info
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record(ctx.stream)
     with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):

@@ -182,6 +182,42 @@ def test_max_dist_masks_exactly_the_reference_pairs(ctx, max_dist):
     assert_T_close(got, ref)
 
 
+def test_pairs_matching_table_finds_the_reference_classes(ctx):
+    """Config 3 at reduced size: 2x2x2 lattice of cubes (pitch = multiple of the cell size), each
+    5x5x5 cells, anisotropic chi.  The device table must find exactly the classes np.unique finds
+    in the reference (demag.py:306-308) and reproduce the dense matrix."""
+    parts = []
+    for ix in range(2):
+        for iy in range(2):
+            for iz in range(2):
+                parts.append(oref.mesh_cuboid_arrays((1e-3,) * 3, (5, 5, 5), position=(1.5e-3 * ix, 1.5e-3 * iy, 1.5e-3 * iz)))
+    pos, quat, dim = (np.vstack([p[k] for p in parts]) for k in range(3))
+    n = len(pos)
+    chi = np.tile((0.3, 0.2, 0.1), n)
+    uniq_ref, inv_ref = oref.match_pairs_indices(pos, quat, dim)
+    from magpylib_material_response_b200.demag import _source_classes
+
+    cls = torch.from_numpy(_source_classes(quat, dim)).to(ctx.device)
+    d_pos, d_quat, d_dim, d_chi = (dev(ctx, a) for a in (pos, quat, dim, chi))
+    ld = 3 * n + 8
+    out = ctx.empty(3 * n, ld)
+    nuniq = ctx.assemble_matched(d_pos, d_quat, d_dim, cls, out, ld, chi=d_chi)
+    assert nuniq == len(uniq_ref)
+    assert nuniq <= (2 * 20 - 1) ** 3
+    dense = assemble_numpy(ctx, pos, quat, dim, chi_cell_major=chi)
+    got = out[:, : 3 * n].cpu().numpy()
+    assert_T_close(got, dense)
+    # members of one class carry bit-identical blocks (copied from the representative)
+    blocks = got.reshape(n, 3, n, 3).transpose(2, 0, 1, 3).reshape(n * n, 9)  # flat index i*n+j
+    offdiag = np.ones(n * n, dtype=bool)
+    offdiag[:: n + 1] = False  # the self pairs carry the "+1" of Q = I - chi N
+    rep_blocks = blocks[uniq_ref][inv_ref]
+    # every cell has the same chi triple, so same class => bit-identical Q block
+    np.testing.assert_array_equal(blocks[offdiag], rep_blocks[offdiag])
+    # a too-small table is reported, not silently wrong
+    assert ctx.assemble_matched(d_pos, d_quat, d_dim, cls, out, ld, chi=d_chi, table_cap_slots=1024) is None
+
+
 def test_block_cyclic_target_sets_tile_the_full_matrix(ctx):
     """Row-block sharding used by the multi-GPU path: the union of all parts == the full matrix."""
     pos, quat, dim, chi, _ = random_cells(100, seed=11)
@@ -443,3 +479,41 @@ def test_config2prime_8000_cells_properties(ctx):
     # physics: mean J_z between the n=1000 (3.5716) and n=2744 (3.5948) values of SURVEY 8c, x/y vanish
     assert 3.55 < J_lu[:, 2].mean() < 3.65
     assert abs(J_lu[:, 0].mean()) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------
+# distributed entry points on ONE rank (the panel-by-panel code path; R > 1 is exercised by
+# tests/multi_gpu_parity.py under torchrun and by the gloo CPU tests)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize(("n", "tgt_block"), [(50, 8), (333, 40), (700, 42)])
+def test_lu_solve_dist_single_rank_vs_numpy(ctx, n, tgt_block):
+    N = 3 * n
+    rng = np.random.default_rng(n)
+    Q = rng.normal(size=(N, N))
+    b = rng.normal(size=N)
+    ld = (N + 15) // 16 * 16
+    dQ = torch.zeros(N, ld, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    dx = dev(ctx, b)
+    info = ctx.lu_solve_dist(N, N, tgt_block, dQ, ld, dx)
+    assert info == 0
+    x = dx.cpu().numpy()
+    resid = np.linalg.norm(Q @ x - b) / (np.linalg.norm(Q) * np.linalg.norm(x))
+    assert resid < 1e-14, resid
+
+
+def test_gmres_dist_single_rank_matches_gmres(ctx):
+    n, tgt_block = 200, 40
+    pos, quat, dim = oref.mesh_cuboid_arrays((1e-3, 2e-3, 1e-3), (5, 8, 5))
+    chi = np.full(3 * n, 50.0)
+    Q = assemble_numpy(ctx, pos, quat, dim, chi_cell_major=chi)
+    N = 3 * n
+    ld = (N + 15) // 16 * 16
+    dQ = torch.zeros(N, ld, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    b = np.tile((0.0, 0.0, 50.0), n)
+    db = dev(ctx, b)
+    dx = torch.zeros_like(db)
+    iters, relres = ctx.gmres_dist(N, N, tgt_block, dQ, ld, db, dx, tol=1e-13, restart=100, maxit=1000)
+    assert relres <= 1e-13
+    np.testing.assert_allclose(dx.cpu().numpy(), np.linalg.solve(Q, b), rtol=1e-9, atol=1e-11)
