@@ -250,7 +250,9 @@ def run_ours(args):
     ld = _padded_ld(N)
 
     # row-block ownership (block-cyclic over cells); single GPU owns everything
-    tgt_block = 64 if world > 1 else n
+    from magpylib_material_response_b200.distributed import DEFAULT_TGT_BLOCK
+
+    tgt_block = DEFAULT_TGT_BLOCK if world > 1 else n
     nblk = -(-n // tgt_block)
     my_blocks = list(range(rank, nblk, world))
     n_local = sum(min(tgt_block, n - b * tgt_block) for b in my_blocks)
@@ -258,8 +260,6 @@ def run_ours(args):
     ipiv = ctx.empty(N, dtype=torch.int32)
     d_x = ctx.empty(N)
     solver = args.solver
-    if world > 1 and solver == "lu" and not args.dist_lu:
-        solver = "gmres"  # distributed LU is selected explicitly; default multi-GPU solver is GMRES
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device) if 8.0 * N * ld * 3 < 512e6 else None
 
     def step():
@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="two_magnets_<n> | soft_cube_<n>")
     ap.add_argument("--solver", default="lu", choices=["lu", "gmres"])
-    ap.add_argument("--dist-lu", action="store_true", help="use the distributed LU for --gpus > 1")
+    ap.add_argument("--dist-lu", action="store_true", help="(kept for compatibility; the distributed LU is the default)")
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
