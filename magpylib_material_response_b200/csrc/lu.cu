@@ -15,6 +15,8 @@
 //   row swaps on the columns outside the panel, TRSM (U12 = L11^-1 A12), DMMA trailing update.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "dgemm.cuh"
 
 namespace cg = cooperative_groups;
@@ -813,6 +815,38 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     attr_set[which] = true;
   }
   dim3 grid((unsigned)ceil_div64(m, BM), (unsigned)ceil_div64(n, BN));
+  const int64_t ntiles = (int64_t)grid.x * grid.y;
+  static int persistent = -1;
+  if (persistent < 0) {
+    const char* e = getenv("MMR_DGEMM_PERSISTENT");
+    persistent = (e && e[0] == '1') ? 1 : 0;  // experiment, off by default (slower than the fast kernel)
+    MMR_CUDA(cudaFuncSetAttribute(dgemm_lu_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MMR_CUDA(cudaFuncSetAttribute(dgemm_lu_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  }
+  static int fast = -1;
+  if (fast < 0) {
+    const char* e = getenv("MMR_DGEMM_FAST");
+    fast = (e && e[0] == '0') ? 0 : 1;
+    MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  }
+  if (fast && aligned && k > 0 && k % BK == 0) {
+    if (subtract)
+      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else
+      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc);
+    MMR_CHECK_LAUNCH(ctx);
+    return 0;
+  }
+  if (subtract && persistent && ntiles > 2 * (int64_t)ctx->sm_count) {
+    const unsigned pg = (unsigned)(2 * ctx->sm_count);
+    if (aligned)
+      dgemm_lu_persistent_kernel<true><<<pg, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, A, lda, B, ldb, C, ldc);
+    else
+      dgemm_lu_persistent_kernel<false><<<pg, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, A, lda, B, ldb, C, ldc);
+    MMR_CHECK_LAUNCH(ctx);
+    return 0;
+  }
   kerns[which]<<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
@@ -996,16 +1030,19 @@ int mmr_lu_trsm(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, i
   return 0;
 }
 
+namespace {
+__global__ void lu_set_identity_kernel(double* __restrict__ X, int nb) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nb * nb) X[e] = (e % nb == e / nb) ? 1.0 : 0.0;
+}
+}  // namespace
+
+// X = L11^-1 as the solution of L11 X = I with the blocked TRSM kernel (nb/32 CTAs, L11 in shared
+// memory).  (The first version used a one-CTA column-per-thread substitution: 304 us per panel.)
 int mmr_lu_trtri(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, int nb, double* X) {
-  const size_t smem = (size_t)nb * (nb + 1) * sizeof(double);
-  static size_t cap = 0;
-  if (smem > cap) {
-    MMR_CUDA(cudaFuncSetAttribute(lu_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cap = smem;
-  }
-  lu_trtri_kernel<<<1, NB, smem, strm>>>(L, ldl, nb, X);
+  lu_set_identity_kernel<<<(unsigned)ceil_div64((int64_t)nb * nb, 256), 256, 0, strm>>>(X, nb);
   MMR_CHECK_LAUNCH(ctx);
-  return 0;
+  return mmr_lu_trsm(ctx, strm, L, ldl, nb, X, nb, nb);
 }
 
 extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld, int32_t* d_ipiv,
