@@ -346,20 +346,27 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    tpath = ROOT / "profiles" / "ncu_traffic_r1.json"
+    traffic = json.loads(tpath.read_text()) if tpath.exists() else {}
     asm_ms, asm_pairs, asm_cnt = prof["assemble"]
     gemm_ms, gemm_flops, gemm_cnt = prof["gemm"]
     mv_ms, mv_bytes, mv_cnt = prof["matvec"]
     fpp = FLOP_PER_PAIR_ROTATED if rotated else FLOP_PER_PAIR_ALIGNED
     roof_asm = {"bound": "fp64", "achieved": asm_pairs * fpp / (asm_ms * 1e-3) / 1e12 if asm_ms else None,
                 "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s (flop-equivalents, SURVEY 8d convention)",
-                "traffic": None, "kernel": "assemble_cell_major_kernel", "ms_per_launch": asm_ms / max(1, asm_cnt),
+                "traffic": traffic.get("assemble_cell_major", {}).get("ratio", 0) * 72.0 * asm_pairs / max(1, asm_cnt) or None,
+                "traffic_src": "72 B/pair x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
+                "kernel": "assemble_cell_major_kernel", "ms_per_launch": asm_ms / max(1, asm_cnt),
                 "entries_per_s": 9.0 * asm_pairs / (asm_ms * 1e-3) if asm_ms else None, "peak_src": peaks["fp64_src"]}
     if roof_asm["achieved"]:
         roof_asm["frac"] = roof_asm["achieved"] / roof_asm["peak"]
     if solver == "lu" and gemm_ms:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["fp64_dmma_tflops"], "traffic": None, "kernel": "dgemm_nn_kernel (LU trailing update, DMMA.8x8x4)",
+                    "frac": ach / peaks["fp64_dmma_tflops"],
+                    "traffic": traffic.get("dgemm_nn", {}).get("ratio", 0) * (gemm_flops / 16.0) / gemm_cnt or None,
+                    "traffic_src": "C read+write bytes (= flops/16 at k=128) x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
+                    "kernel": "dgemm_nn_fast_kernel (LU trailing update, DMMA.8x8x4)",
                     "launches": gemm_cnt, "ms_per_launch": gemm_ms / gemm_cnt,
                     "peak_src": "FP64 DMMA peak " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry"}
     elif mv_ms:

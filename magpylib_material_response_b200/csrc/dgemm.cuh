@@ -211,7 +211,7 @@ template <bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_fast_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                          const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                         int64_t ldc) {
+                         int64_t ldc, int stagger_ns, int sm_count) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
@@ -219,6 +219,13 @@ __global__ void __launch_bounds__(THREADS, 2)
   const int wm = warp & 3, wn = warp >> 2;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int KT = k / BK;
+  // De-phase the two CTAs that share an SM: in the first wave the second CTA of every SM starts
+  // half a tile later; every later CTA inherits the offset of the slot it replaces, so one CTA's
+  // load/store phases fall into the other's DMMA phase instead of coinciding with them.
+  if (stagger_ns > 0) {
+    const int lin = blockIdx.x + blockIdx.y * gridDim.x;
+    if (lin >= sm_count && lin < 2 * sm_count) __nanosleep(stagger_ns);
+  }
 
   double acc[4][4][2];
   if (SUBTRACT) {

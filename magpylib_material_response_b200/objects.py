@@ -48,7 +48,10 @@ class Style:
         return {k: (v.as_dict() if isinstance(v, Style) else v) for k, v in vars(self).items()}
 
     def copy(self):
-        return _copy.deepcopy(self)
+        new = Style.__new__(Style)
+        for k, v in vars(self).items():
+            new.__dict__[k] = v.copy() if isinstance(v, Style) else (_copy.deepcopy(v) if isinstance(v, dict | list) else v)
+        return new
 
     def __repr__(self):
         return f"Style({self.as_dict()})"
@@ -210,6 +213,12 @@ class BaseGeo:
                 new._parent = memo.get(id(v)) if v is not None else None
             elif k == "_orientation":
                 new._orientation = v  # Rotation objects are immutable
+            elif isinstance(v, np.ndarray):
+                new.__dict__[k] = v.copy()
+            elif v is None or isinstance(v, int | float | str | bool | tuple):
+                new.__dict__[k] = v  # immutable (tuples of numbers: susceptibility, H_ext)
+            elif isinstance(v, Style):
+                new.__dict__[k] = v.copy()
             else:
                 setattr(new, k, _copy.deepcopy(v, memo))
         BaseGeo._ids += 1

@@ -517,3 +517,23 @@ def test_gmres_dist_single_rank_matches_gmres(ctx):
     iters, relres = ctx.gmres_dist(N, N, tgt_block, dQ, ld, db, dx, tol=1e-13, restart=100, maxit=1000)
     assert relres <= 1e-13
     np.testing.assert_allclose(dx.cpu().numpy(), np.linalg.solve(Q, b), rtol=1e-9, atol=1e-11)
+
+
+def test_lu_large_panel_fallback_path(ctx):
+    """N > 25600 rows: the early strips exceed the single-cluster capacity and go through the
+    cooperative grid-barrier kernel (the path every early panel of the 64k-cell config takes)."""
+    N = 26000
+    g = torch.Generator(device=ctx.device)
+    g.manual_seed(1)
+    ld = (N + 15) // 16 * 16
+    Q = torch.randn(N, ld, dtype=torch.float64, device=ctx.device, generator=g)
+    b = torch.randn(N, dtype=torch.float64, device=ctx.device, generator=g)
+    Q0 = Q.clone()
+    ipiv = torch.zeros(N, dtype=torch.int32, device=ctx.device)
+    assert ctx.lu_factor(Q, ld, ipiv) == 0
+    x = b.clone()
+    ctx.lu_solve(Q, ld, ipiv, x)
+    y = torch.empty_like(b)
+    ctx.matvec(Q0, ld, x, y)
+    resid = float(torch.linalg.norm(y - b) / (torch.linalg.norm(Q0[:, :N]) * torch.linalg.norm(x)))
+    assert resid < 1e-14, resid
