@@ -1291,39 +1291,70 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
   const size_t linv_bytes = sizeof(double) * NB * NB;
   const size_t ipiv_bytes = ((sizeof(int) * (size_t)N + 255) / 256) * 256;
-  const size_t p_bytes = sizeof(double) * (size_t)N * nbw;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + linv_bytes + ipiv_bytes + p_bytes + sizeof(double) * (size_t)N + 512);
+  const size_t p_bytes = ((sizeof(double) * (size_t)N * nbw + 255) / 256) * 256;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes + 2 * p_bytes + sizeof(double) * (size_t)N + 512);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
   if (rc) return rc;
   char* base = (char*)ctx->ws;
   int* d_info = (int*)base;
   void* scratch = base + 256;
-  double* Linv = (double*)(base + 256 + scratch_bytes);
-  int* d_ipiv = (int*)(base + 256 + scratch_bytes + linv_bytes);
-  double* P = (double*)(base + 256 + scratch_bytes + linv_bytes + ipiv_bytes);
-  double* d_tmp = P + (size_t)N * nbw;
+  double* Linv2[2] = {(double*)(base + 256 + scratch_bytes), (double*)(base + 256 + scratch_bytes + linv_bytes)};
+  int* d_ipiv = (int*)(base + 256 + scratch_bytes + 2 * linv_bytes);
+  double* P2[2] = {(double*)(base + 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes),
+                   (double*)(base + 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes + p_bytes)};
+  double* d_tmp = (double*)(base + 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes + 2 * p_bytes);
   MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
   double* Al = d_Qlocal;
+  cudaStream_t side = ctx->side;
 
+  // factor global panel s (owned by this rank) on stream `strm`, invert its diagonal block and pack it
+  auto factor_and_pack = [&](int s, cudaStream_t strm) -> int {
+    const int kb = s * nbw, nb = min(nbw, N - kb), m = N - kb;
+    double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;  // global column kb -> my local column
+    int r = mmr_lu_panel(ctx, strm, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
+    if (r) return r;
+    r = mmr_lu_trtri(ctx, strm, Ash + (int64_t)kb * ld + kb, ld, nb, Linv2[s & 1]);
+    if (r) return r;
+    MMR_CUDA(cudaMemcpy2DAsync(P2[s & 1], sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
+                               sizeof(double) * m, nb, cudaMemcpyDeviceToDevice, strm));
+    return 0;
+  };
+  // apply panel s (pivots, U12 = L11^-1 A12, A22 -= L21 U12) to my local columns [c0, c1)
+  auto update_local = [&](int s, int c0, int c1) -> int {
+    if (c1 <= c0) return 0;
+    const int kb = s * nbw, nb = min(nbw, N - kb), m = N - kb;
+    const double* P = P2[s & 1];
+    int r = mmr_lu_laswp(ctx, st, Al, ld, kb, kb + nb, c0, c1, d_ipiv);
+    if (r) return r;
+    int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
+    r = mmr_dgemm_launch(ctx, st, nb, c1 - c0, nb, 1.0, Linv2[s & 1], nb, Al + (int64_t)c0 * ld + kb, ld, 0.0,
+                         Al + (int64_t)c0 * ld + kb, ld);
+    if (r) return r;
+    mmr_prof_end(ctx, ps, 2.0 * nb * nb * (c1 - c0), st);
+    if (m > nb) {
+      ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);
+      r = mmr_dgemm_launch(ctx, st, m - nb, c1 - c0, nb, -1.0, P + nb, m, Al + (int64_t)c0 * ld + kb, ld, 1.0,
+                           Al + (int64_t)c0 * ld + kb + nb, ld);
+      if (r) return r;
+      mmr_prof_end(ctx, ps, 2.0 * (m - nb) * (double)(c1 - c0) * nb, st);
+    }
+    return 0;
+  };
+
+  if (me == 0) {
+    rc = factor_and_pack(0, st);
+    if (rc) return rc;
+  }
   for (int s = 0; s < S; ++s) {
     const int kb = s * nbw;
     const int nb = min(nbw, N - kb);
     const int m = N - kb;
     const int owner = s % R;
-    if (me == owner) {
-      double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;  // global column kb -> my local column
-      rc = mmr_lu_panel(ctx, st, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
-      if (rc) return rc;
-      rc = mmr_lu_trtri(ctx, st, Ash + (int64_t)kb * ld + kb, ld, nb, Linv);
-      if (rc) return rc;
-      MMR_CUDA(cudaMemcpy2DAsync(P, sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
-                                 sizeof(double) * m, nb, cudaMemcpyDeviceToDevice, st));
-    }
     if (R > 1) {
-      rc = mmr_comm_bcast_bytes(ctx, P, sizeof(double) * (size_t)m * nb, owner, st);
+      rc = mmr_comm_bcast_bytes(ctx, P2[s & 1], sizeof(double) * (size_t)m * nb, owner, st);
       if (rc) return rc;
-      rc = mmr_comm_bcast_bytes(ctx, Linv, sizeof(double) * (size_t)nb * nb, owner, st);
+      rc = mmr_comm_bcast_bytes(ctx, Linv2[s & 1], sizeof(double) * (size_t)nb * nb, owner, st);
       if (rc) return rc;
       rc = mmr_comm_bcast_bytes(ctx, d_ipiv + kb, sizeof(int) * (size_t)nb, owner, st);
       if (rc) return rc;
@@ -1335,21 +1366,24 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
     // my trailing panels (global index > s)
     const int first_trail = (s >= me) ? ((s - me) / R + 1) : 0;
     const int ct0 = first_trail * nbw, ct1 = ncols_local;
-    if (ct1 > ct0) {
-      rc = mmr_lu_laswp(ctx, st, Al, ld, kb, kb + nb, ct0, ct1, d_ipiv);
+    const bool own_next = (s + 1 < S) && ((s + 1) % R == me);
+    if (own_next) {
+      // look-ahead: bring my block of panel s+1 up to date first, factor it on the side stream while
+      // the main stream updates the rest of my trailing columns
+      const int nb1 = min(nbw, N - (s + 1) * nbw);
+      rc = update_local(s, ct0, ct0 + nb1);
       if (rc) return rc;
-      int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
-      rc = mmr_dgemm_launch(ctx, st, nb, ct1 - ct0, nb, 1.0, Linv, nb, Al + (int64_t)ct0 * ld + kb, ld, 0.0,
-                            Al + (int64_t)ct0 * ld + kb, ld);
+      MMR_CUDA(cudaEventRecord(ctx->ev[0], st));
+      MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
+      rc = factor_and_pack(s + 1, side);
       if (rc) return rc;
-      mmr_prof_end(ctx, ps, 2.0 * nb * nb * (ct1 - ct0), st);
-      if (m > nb) {
-        ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);
-        rc = mmr_dgemm_launch(ctx, st, m - nb, ct1 - ct0, nb, -1.0, P + nb, m, Al + (int64_t)ct0 * ld + kb, ld, 1.0,
-                              Al + (int64_t)ct0 * ld + kb + nb, ld);
-        if (rc) return rc;
-        mmr_prof_end(ctx, ps, 2.0 * (m - nb) * (double)(ct1 - ct0) * nb, st);
-      }
+      MMR_CUDA(cudaEventRecord(ctx->ev[1], side));
+      rc = update_local(s, ct0 + nb1, ct1);
+      if (rc) return rc;
+      MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[1], 0));
+    } else {
+      rc = update_local(s, ct0, ct1);
+      if (rc) return rc;
     }
   }
 
