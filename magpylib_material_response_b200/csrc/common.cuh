@@ -44,6 +44,7 @@ struct mmr_ctx {
   // side stream + events for look-ahead in the LU
   cudaStream_t side = nullptr;
   bool lookahead = true;
+  void* laswp_buf = nullptr;  // LaswpPerm scratch (lu.cu)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 

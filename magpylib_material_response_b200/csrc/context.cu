@@ -171,6 +171,7 @@ extern "C" int mmr_ctx_destroy(mmr_ctx* ctx) {
     cudaEventDestroy(r.e1);
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+  if (ctx->laswp_buf) cudaFree(ctx->laswp_buf);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->hpin) cudaFreeHost(ctx->hpin);

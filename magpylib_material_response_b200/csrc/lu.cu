@@ -619,25 +619,6 @@ __global__ void lu_panel_swap_trsm_kernel(double* __restrict__ A, int64_t ld, in
   }
 }
 
-// Row swaps ipiv[k0..k1) applied to columns [col_begin, col_end): one thread per column.
-__global__ void lu_laswp_kernel(double* __restrict__ A, int64_t ld, int k0, int k1, int col_begin,
-                                int col_end, const int* __restrict__ ipiv) {
-  extern __shared__ int s_piv[];
-  for (int i = threadIdx.x; i < k1 - k0; i += blockDim.x) s_piv[i] = ipiv[k0 + i];
-  __syncthreads();
-  const int col = col_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= col_end) return;
-  double* a = A + (int64_t)col * ld;
-  for (int i = 0; i < k1 - k0; ++i) {
-    const int p = s_piv[i];
-    if (p != k0 + i) {
-      const double tmp = a[k0 + i];
-      a[k0 + i] = a[p];
-      a[p] = tmp;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // TRSM: B (nb x ncols, column-major, ldb) <- L^-1 B with L = unit lower nb x nb block of the
 // factored panel (column-major, ldl).  One CTA per TRSM_COLS columns of B, B block in shared
@@ -707,33 +688,6 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------
-// X = L^-1 for the unit-lower nb x nb diagonal block of a factored panel (column-major L, ldl).
-// One CTA, one thread per column of X (forward substitution); X is kept in shared memory and
-// written out as a dense nb x nb column-major matrix (upper part zero).  Runs on the look-ahead
-// stream, so the main stream's "TRSM" becomes a plain DMMA GEMM U12 = X * A12.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB)
-    lu_trtri_kernel(const double* __restrict__ L, int64_t ldl, int nb, double* __restrict__ X) {
-  extern __shared__ __align__(16) double Xs[];  // Xs[c*(nb+1) + r]
-  const int c = threadIdx.x;
-  if (c < nb) {
-    double* x = Xs + c * (nb + 1);
-    for (int r = 0; r < c; ++r) x[r] = 0.0;
-    x[c] = 1.0;
-    for (int r = c + 1; r < nb; ++r) {
-      double acc = L[(int64_t)c * ldl + r];  // t = c term (x[c] = 1)
-      for (int t = c + 1; t < r; ++t) acc += L[(int64_t)t * ldl + r] * x[t];
-      x[r] = -acc;
-    }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int r = e % nb, cc = e / nb;
-    X[(int64_t)cc * nb + r] = Xs[cc * (nb + 1) + r];
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // Triangular solves for Q x = b with Q^T = A = P L U:  U^T w = b,  L^T v = w,  x = P v.
 // Each "row" of U^T / L^T is a contiguous column of A, so the off-diagonal part is a
 // coalesced dot-product GEMV (one warp per column), the diagonal block a small serial solve.
@@ -756,35 +710,78 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) b[c] -= acc;
 }
 
-// Solve the SB x SB diagonal block in place (single CTA of SB threads, block transposed into
-// dynamic shared memory).
+// Solve the SB x SB diagonal block in place (one CTA; block staged in dynamic shared memory).
 //   UPPER_T: w[c] = (b[c] - sum_{k0<=r<c} A[r,c] w[r]) / A[c,c]      ascending c
 //   else   : v[c] =  b[c] - sum_{c<r<k1} A[r,c] v[r]                 descending c (unit diag)
+// The needed triangle is fetched by 512 threads with 8 independent loads in flight each (the
+// first version's 128 threads x 128 dependent iterations cost ~30 us of pure DRAM latency per
+// block), the next block on the walk is prefetched into L2, and the substitution runs in 32 x 32
+// sub-blocks: one warp solves a sub-block with register-resident columns and shuffles, then 128
+// threads eliminate it from the rest of the block.
+constexpr int DIAG_THREADS = 512;
 template <bool UPPER_T>
-__global__ void __launch_bounds__(SB)
-    lu_diag_solve_kernel(const double* __restrict__ A, int64_t ld, int k0, int k1,
+__global__ void __launch_bounds__(DIAG_THREADS)
+    lu_diag_solve_kernel(const double* __restrict__ A, int64_t ld, int k0, int k1, int N,
                          double* __restrict__ b) {
   extern __shared__ __align__(16) double T[];  // T[r*(SB+1) + c] = A[k0+r, k0+c]
   __shared__ double x[SB];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbk = k1 - k0;
-  for (int c = 0; c < nbk; ++c) {
-    if (tid < nbk) T[tid * (SB + 1) + c] = A[(int64_t)(k0 + c) * ld + k0 + tid];
+#pragma unroll 8
+  for (int i = 0; i < SB * SB / DIAG_THREADS; ++i) {
+    const int e = tid + i * DIAG_THREADS;
+    const int r = e % SB, c = e / SB;
+    const bool need = UPPER_T ? (r <= c) : (r > c);
+    if (need && r < nbk && c < nbk) T[r * (SB + 1) + c] = A[(int64_t)(k0 + c) * ld + k0 + r];
   }
   if (tid < nbk) x[tid] = b[k0 + tid];
+  {  // L2 prefetch of the next diagonal block on the walk (8 lines of 128 B per column)
+    const int nk0 = UPPER_T ? k0 + SB : k0 - SB;
+    if (nk0 >= 0 && nk0 < N) {
+      for (int line = tid; line < SB * 8; line += DIAG_THREADS) {
+        const int c = nk0 + (line >> 3), r = nk0 + (line & 7) * 16;
+        if (c < N && r < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (int64_t)c * ld + r));
+      }
+    }
+  }
   __syncthreads();
-  if (UPPER_T) {
-    for (int r = 0; r < nbk; ++r) {
-      if (tid == r) x[r] = x[r] / T[r * (SB + 1) + r];
-      __syncthreads();
-      if (tid > r && tid < nbk) x[tid] -= T[r * (SB + 1) + tid] * x[r];
-      __syncthreads();
+  const int nsub = (nbk + 31) / 32;
+  for (int q = 0; q < nsub; ++q) {
+    const int sb = UPPER_T ? 32 * q : 32 * (nsub - 1 - q);
+    const int len = min(32, nbk - sb);
+    if (warp == 0) {
+      const int c = sb + lane;
+      double xv = (lane < len) ? x[c] : 0.0;
+      double tc[32];  // column c of the sub-block: T[sb + r][c]
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const bool need = UPPER_T ? (r < lane) : (r > lane);
+        tc[r] = (need && r < len && lane < len) ? T[(sb + r) * (SB + 1) + c] : 0.0;
+      }
+      if (UPPER_T) {
+        const double rd = (lane < len) ? 1.0 / T[c * (SB + 1) + c] : 1.0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const double xr = __shfl_sync(0xffffffffu, xv, r) * __shfl_sync(0xffffffffu, rd, r);
+          if (lane == r) xv = xr;
+          xv -= tc[r] * xr;  // tc[r] == 0 for lanes <= r
+        }
+      } else {
+#pragma unroll
+        for (int r = 31; r >= 0; --r) {
+          const double xr = __shfl_sync(0xffffffffu, xv, r);
+          xv -= tc[r] * xr;  // tc[r] == 0 for lanes >= r
+        }
+      }
+      if (lane < len) x[c] = xv;
     }
-  } else {
-    for (int r = nbk - 1; r >= 0; --r) {
-      if (tid < r) x[tid] -= T[r * (SB + 1) + tid] * x[r];
-      __syncthreads();
+    __syncthreads();
+    if (tid < nbk && (UPPER_T ? (tid >= sb + 32) : (tid < sb))) {
+      double acc = x[tid];
+      for (int r = sb; r < sb + len; ++r) acc -= T[r * (SB + 1) + tid] * x[r];
+      x[tid] = acc;
     }
+    __syncthreads();
   }
   if (tid < nbk) b[k0 + tid] = x[tid];
 }
@@ -1016,14 +1013,425 @@ int mmr_lu_panel(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, 
 
 size_t mmr_lu_panel_scratch_bytes() { return 2 * 256 * sizeof(Cand) + (2 * 256 * W + 2 * W) * sizeof(double); }
 
+// =======================================================================================
+// Speculative panel: "the pivot is on the diagonal" (true for the demag matrices Q = I - chi*T
+// of every BASELINE config), verified a posteriori.
+//
+//   1. lu_diag_nopiv_kernel   LU without interchanges of the nb x nb diagonal block (one CTA)
+//   2. lu_tri_inv_kernel      L11^-1 and U11^-1                                   (8 CTAs)
+//   3. DMMA GEMM              L21 = A21 * U11^-1                                   (all SMs)
+//   4. lu_spec_check / commit max |l_ij| <= 1 ?  then copy the packed panel into A, ipiv = identity
+//
+// Partial pivoting picks row j at step j exactly when every multiplier of that step has
+// magnitude <= 1 (ties go to the lowest index = the diagonal, as in LAPACK's idamax), and as long
+// as that holds the partially eliminated matrix is the one of the unpivoted factorization.  So
+// "all |l_ij| <= 1" <=> the pivoted factorization performs no interchange in this panel, and then
+// both produce the same L and U (up to the rounding of a different operation order).  Nothing is
+// written to A before the check, so a failed check simply falls back to the pivoting strip
+// kernels above.  This turns the latency-bound chain of 128 cluster-synchronised column steps
+// (~0.5 ms per panel) into one small CTA kernel plus tensor-core work (~0.1 ms).
+// =======================================================================================
+namespace {
+
+// Thread (r, q) owns row r, columns [q*SEG, (q+1)*SEG) in registers.  Segment q lags q time steps
+// behind segment 0 so that one __syncthreads per step is enough: at time t it applies step
+// j = t - q using the multiplier column published by the pivot segment (ring lcol) and its part of
+// pivot row j (urow), which its thread r = j published at the end of the previous time step.
+// Inside its own pivot phase a segment rotates its registers by one per step (fused into the
+// update), so the current column is always v[0] and no dynamic register indexing is needed.
+template <int SEG>
+__global__ void __launch_bounds__(128 * (128 / SEG), 1)
+    lu_diag_nopiv_kernel(const double* __restrict__ A, int64_t ld, int kb, int nb, double* __restrict__ S,
+                         int64_t lds, int* __restrict__ flag) {
+  constexpr int NQ = 128 / SEG;
+  __shared__ __align__(16) double urow[NQ][2][SEG];
+  __shared__ double lcol[NQ][128];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, r = tid & 127, q = tid >> 7;
+  const int warp_rmax = (r | 31);  // largest row of my warp
+  double v[SEG];
+#pragma unroll
+  for (int c = 0; c < SEG; ++c) {
+    const int gc = q * SEG + c;
+    v[c] = (r < nb && gc < nb) ? A[(int64_t)(kb + gc) * ld + kb + r] : ((r == gc) ? 1.0 : 0.0);
+  }
+  if (tid == 0) s_bad = 0;
+  if (r == 0) {
+#pragma unroll
+    for (int c = 0; c < SEG; ++c) urow[q][0][c] = v[c];
+  }
+  __syncthreads();
+  bool bad = false;
+#pragma unroll 1
+  for (int t = 0; t < 128 + NQ - 1; ++t) {
+    const int j = t - q;  // warp-uniform
+    if (j >= 0 && j < 128) {
+      const int p = j / SEG;
+      const double* u = urow[q][j & 1];
+      if (q == p) {
+        const double piv = u[0];
+        const double rinv = 1.0 / piv;
+        const bool act = r > j;
+        const double l = act ? v[0] * rinv : 0.0;
+        if (piv == 0.0 || (act && !(fabs(l) <= 1.0))) bad = true;
+        const double keep = act ? l : v[0];
+        if (NQ > 1) lcol[j % NQ][r] = l;
+        if (warp_rmax > j) {
+#pragma unroll
+          for (int c = 1; c < SEG; ++c) v[c - 1] = v[c] - l * u[c];
+        } else {  // every row of this warp is already a row of U: rotation only
+#pragma unroll
+          for (int c = 1; c < SEG; ++c) v[c - 1] = v[c];
+        }
+        v[SEG - 1] = keep;
+      } else if (q > p && warp_rmax > j) {
+        const double l = lcol[j % NQ][r];
+#pragma unroll
+        for (int c = 0; c < SEG; ++c) v[c] -= l * u[c];
+      }
+      // publish my part of pivot row j+1 for my segment's next step
+      const int jn = j + 1;
+      if (r == jn && jn < 128 && q >= jn / SEG) {
+        const int valid = (q == jn / SEG) ? SEG - (jn - q * SEG) : SEG;  // rotated positions still to update
+        double* un = urow[q][jn & 1];
+#pragma unroll
+        for (int c = 0; c < SEG; ++c) un[c] = (c < valid) ? v[c] : 0.0;
+      }
+    }
+    __syncthreads();
+  }
+  if (bad) s_bad = 1;
+  __syncthreads();
+  if (tid == 0) *flag = s_bad;
+#pragma unroll
+  for (int c = 0; c < SEG; ++c) {
+    const int gc = q * SEG + c;
+    if (r < nb && gc < nb) S[(int64_t)gc * lds + r] = v[c];
+  }
+}
+
+// Inverses of the two triangular factors packed in S (nb x nb, ld lds): blockIdx.y = 0: X = L^-1
+// (unit lower), 1: X = U^-1 through Y = (U^T)^-1 (lower, explicit diagonal), X = Y^T.  One CTA per
+// 32 columns of the lower-triangular inverse; blocked forward substitution on the identity, rows
+// above the first column of the block are zero and skipped.  Output: dense nb x nb, ld = nb.
+constexpr int TINV_COLS = 32;
+__global__ void __launch_bounds__(256)
+    lu_tri_inv_kernel(const double* __restrict__ S, int64_t lds, int nb, double* __restrict__ Linv,
+                      double* __restrict__ Uinv) {
+  extern __shared__ __align__(16) double sm[];
+  double* Bs = sm;                          // [TINV_COLS][nb+1]
+  double* Ls = sm + TINV_COLS * (nb + 1);   // Ls[c*(nb+1) + r], r >= c
+  const bool upper = blockIdx.y == 1;
+  const int tid = threadIdx.x;
+  const int cb = blockIdx.x * TINV_COLS;
+  const int nc = min(TINV_COLS, nb - cb);
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
+    const int r = e % nb, c = e / nb;
+    double val = 0.0;
+    if (upper) {
+      // lower-triangular T = U^T: T(r, c) = U(c, r) = S[r*lds + c]; read coalesced along the fast index
+      const int rr = e / nb, cc = e % nb;  // (row rr, col cc) of T with cc fastest
+      if (rr >= cc) Ls[cc * (nb + 1) + rr] = S[(int64_t)rr * lds + cc];
+      continue;
+    }
+    if (r > c) val = S[(int64_t)c * lds + r];
+    else if (r == c) val = 1.0;
+    if (r >= c) Ls[c * (nb + 1) + r] = val;
+  }
+  for (int e = tid; e < nc * nb; e += blockDim.x) {
+    const int r = e % nb, c = e / nb;
+    Bs[c * (nb + 1) + r] = (r == cb + c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  constexpr int TB = 16;
+  const int c = tid % TINV_COLS;
+  const int rg = tid / TINV_COLS;
+  constexpr int RG = 256 / TINV_COLS;
+  for (int t0 = (cb / TB) * TB; t0 < nb; t0 += TB) {
+    const int tb = min(TB, nb - t0);
+    if (tid < nc) {
+      double x[TB];
+#pragma unroll
+      for (int i = 0; i < TB; ++i) x[i] = (i < tb) ? Bs[tid * (nb + 1) + t0 + i] : 0.0;
+#pragma unroll
+      for (int i = 0; i < TB; ++i) {
+        if (i < tb) {
+#pragma unroll
+          for (int qq = 0; qq < i; ++qq) x[i] -= Ls[(t0 + qq) * (nb + 1) + t0 + i] * x[qq];
+          x[i] /= Ls[(t0 + i) * (nb + 1) + t0 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TB; ++i)
+        if (i < tb) Bs[tid * (nb + 1) + t0 + i] = x[i];
+    }
+    __syncthreads();
+    if (c < nc && t0 + tb < nb) {
+      double x[TB];
+#pragma unroll
+      for (int i = 0; i < TB; ++i) x[i] = (i < tb) ? Bs[c * (nb + 1) + t0 + i] : 0.0;
+      for (int r = t0 + tb + rg; r < nb; r += RG) {
+        double acc = 0.0;
+#pragma unroll
+        for (int qq = 0; qq < TB; ++qq)
+          if (qq < tb) acc += Ls[(t0 + qq) * (nb + 1) + r] * x[qq];
+        Bs[c * (nb + 1) + r] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+  // Bs[c][r] = Y(r, cb + c).  L: X(r, cb+c) = Y(r, cb+c);  U: X(cb+c, r) = Y(r, cb+c)
+  for (int e = tid; e < nc * nb; e += blockDim.x) {
+    const int r = e % nb, cc = e / nb;
+    const double val = Bs[cc * (nb + 1) + r];
+    if (upper) Uinv[(int64_t)r * nb + cb + cc] = val;
+    else Linv[(int64_t)(cb + cc) * nb + r] = val;
+  }
+}
+
+// flag |= any |S[r, c]| > 1 (or NaN) for r in [r0, m), c in [0, nb)
+__global__ void __launch_bounds__(256)
+    lu_spec_check_kernel(const double* __restrict__ S, int64_t lds, int r0, int m, int nb, int* __restrict__ flag) {
+  const int64_t rows = m - r0;
+  const int64_t total = rows * nb;
+  bool bad = false;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % rows, c = e / rows;
+    bad |= !(fabs(S[c * lds + r0 + r]) <= 1.0);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// if (*flag == 0): A[kb + r, kb + c] = S[r, c] for r < m, c < nb; ipiv[kb + c] = kb + c
+__global__ void __launch_bounds__(256)
+    lu_spec_commit_kernel(const double* __restrict__ S, int64_t lds, int m, int nb, double* __restrict__ A,
+                          int64_t ld, int kb, int* __restrict__ ipiv, const int* __restrict__ flag) {
+  if (*flag != 0) return;
+  const int64_t total = (int64_t)m * nb;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % m, c = e / m;
+    A[(kb + c) * ld + kb + r] = S[c * lds + r];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < nb) ipiv[kb + threadIdx.x] = kb + threadIdx.x;
+}
+
+}  // namespace
+
+size_t mmr_lu_spec_scratch_bytes() { return sizeof(double) * NB * NB + 256; }  // U11^-1 + flag
+
+// Speculative factorization of the panel columns [kb, kb+nb), rows [kb, N) of A (see above).
+// S: m x nb packed panel buffer (ld = m = N - kb), left filled with the factored panel on success.
+// d_spec: mmr_lu_spec_scratch_bytes() of device scratch.  *ok_out = 1: A, ipiv, Linv and S hold the
+// result; 0: nothing was modified (the caller runs the pivoting path).  Synchronises `strm`.
+int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
+                      double* S, double* Linv, void* d_spec, int* ok_out) {
+  static bool attr = false;
+  const size_t inv_smem = ((size_t)TINV_COLS * (NB + 1) + (size_t)NB * (NB + 1)) * sizeof(double);
+  if (!attr) {
+    MMR_CUDA(cudaFuncSetAttribute(lu_tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+    attr = true;
+  }
+  static int seg = -1;
+  if (seg < 0) {
+    const char* e = getenv("MMR_LU_DIAG_SEG");
+    seg = e ? atoi(e) : 32;
+  }
+  const int m = N - kb;
+  double* Uinv = (double*)d_spec;
+  int* d_flag = (int*)((char*)d_spec + sizeof(double) * NB * NB);
+  const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, strm);
+  if (seg == 64) lu_diag_nopiv_kernel<64><<<1, 256, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
+  else if (seg == 16) lu_diag_nopiv_kernel<16><<<1, 1024, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
+  else lu_diag_nopiv_kernel<32><<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
+  MMR_CHECK_LAUNCH(ctx);
+  const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
+  lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, strm>>>(S, m, nb, Linv, Uinv);
+  MMR_CHECK_LAUNCH(ctx);
+  mmr_prof_end(ctx, pidx, (double)nb, strm);
+  if (m > nb) {
+    const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
+    int rc = mmr_dgemm_launch(ctx, strm, m - nb, nb, nb, 1.0, A + (int64_t)kb * ld + kb + nb, ld, Uinv, nb, 0.0,
+                              S + nb, m);
+    if (rc) return rc;
+    mmr_prof_end(ctx, pg, 2.0 * (m - nb) * (double)nb * nb, strm);
+    const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)(m - nb) * nb, 256 * 8));
+    lu_spec_check_kernel<<<g, 256, 0, strm>>>(S, m, nb, m, nb, d_flag);
+    MMR_CHECK_LAUNCH(ctx);
+  }
+  {
+    const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)m * nb, 256 * 8));
+    lu_spec_commit_kernel<<<g, 256, 0, strm>>>(S, m, m, nb, A, ld, kb, d_ipiv, d_flag);
+    MMR_CHECK_LAUNCH(ctx);
+  }
+  int* h_flag = (int*)((char*)ctx->hpin + 128);
+  MMR_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, strm));
+  MMR_CUDA(cudaStreamSynchronize(strm));
+  *ok_out = (*h_flag == 0) ? 1 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Row interchanges (LAPACK laswp) for general matrices.  The nb sequential swaps of a panel touch at
+// most 2*nb rows; one warp turns the pivot sequence into a permutation of those rows
+// ("the data that ends at row rows[t] comes from row src[t]"), then one warp per column gathers
+// and scatters.  (The first version walked the nb dependent swaps serially per column: 51 ms per
+// factorization of a random 24000^2 matrix.)  Panels without any interchange -- the usual case for
+// the demag matrix Q = I + chi*N -- cost one early-exit launch.
+// ---------------------------------------------------------------------------------------
+namespace {
+constexpr int LASWP_MAX = 2 * NB;
+struct LaswpPerm {
+  int count;
+  int moved;
+  int rows[LASWP_MAX];
+  int src[LASWP_MAX];
+};
+
+__global__ void __launch_bounds__(32)
+    lu_laswp_prepare_kernel(const int* __restrict__ ipiv, int k0, int nb, LaswpPerm* __restrict__ out) {
+  __shared__ int piv[NB], rows[LASWP_MAX], cur[LASWP_MAX];
+  const int lane = threadIdx.x;
+  int any = 0;
+  for (int i = lane; i < nb; i += 32) {
+    const int p = ipiv[k0 + i];
+    piv[i] = p;
+    rows[i] = k0 + i;
+    cur[i] = k0 + i;
+    any |= (p != k0 + i);
+  }
+  if (!__any_sync(0xffffffffu, any)) {  // no interchange in this panel: the usual demag case
+    if (lane == 0) {
+      out->count = 0;
+      out->moved = 0;
+    }
+    return;
+  }
+  int cnt = nb;
+  __syncwarp();
+  for (int i = 0; i < nb; ++i) {
+    const int p = piv[i];
+    if (p == k0 + i) continue;  // warp-uniform
+    int found = -1;
+    for (int t = lane; t < cnt; t += 32)
+      if (rows[t] == p) found = t;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) found = max(found, __shfl_xor_sync(0xffffffffu, found, off));
+    if (found < 0) {
+      found = cnt;
+      if (lane == 0) {
+        rows[cnt] = p;
+        cur[cnt] = p;
+      }
+      ++cnt;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int t = cur[i];
+      cur[i] = cur[found];
+      cur[found] = t;
+    }
+    __syncwarp();
+  }
+  // keep only the rows whose content changes (warp-level stream compaction)
+  int kept = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int t = base + lane;
+    const bool mv = (t < cnt) && (rows[t] != cur[t]);
+    const unsigned bal = __ballot_sync(0xffffffffu, mv);
+    if (mv) {
+      const int slot = kept + __popc(bal & ((1u << lane) - 1u));
+      out->rows[slot] = rows[t];
+      out->src[slot] = cur[t];
+    }
+    kept += __popc(bal);
+  }
+  if (lane == 0) {
+    out->count = kept;
+    out->moved = kept > 0;
+  }
+}
+
+// Applies up to two prepared permutations (p0 first, then p1) to the columns [col_begin, col_end):
+// one warp per column gathers the moved rows into registers and scatters them.
+__global__ void __launch_bounds__(256)
+    lu_laswp_apply_kernel(double* __restrict__ A, int64_t ld, int col_begin, int col_end,
+                          const LaswpPerm* __restrict__ p0, const LaswpPerm* __restrict__ p1) {
+  const int m0 = p0->moved, m1 = p1 ? p1->moved : 0;
+  if ((m0 | m1) == 0) return;
+  __shared__ int s_rows[LASWP_MAX], s_src[LASWP_MAX];
+  const int lane = threadIdx.x & 31;
+  const int col = col_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double* a = A + (int64_t)min(col, col_end - 1) * ld;
+  for (int pass = 0; pass < 2; ++pass) {
+    const LaswpPerm* perm = pass ? p1 : p0;
+    if (!(pass ? m1 : m0)) continue;  // block-uniform
+    const int cnt = perm->count;
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+      s_rows[t] = perm->rows[t];
+      s_src[t] = perm->src[t];
+    }
+    __syncthreads();
+    if (col < col_end) {
+      double v[LASWP_MAX / 32];
+#pragma unroll
+      for (int q = 0; q < LASWP_MAX / 32; ++q) {
+        const int t = lane + 32 * q;
+        v[q] = (t < cnt) ? a[s_src[t]] : 0.0;
+      }
+      __syncwarp();  // every gather of this column is performed before any scatter
+#pragma unroll
+      for (int q = 0; q < LASWP_MAX / 32; ++q) {
+        const int t = lane + 32 * q;
+        if (t < cnt) a[s_rows[t]] = v[q];
+      }
+      __syncwarp();  // ... and the scatter before the second permutation's gather
+    }
+  }
+}
+}  // namespace
+
+// Permutation record slots in the context: [0], [1] = scratch of mmr_lu_laswp (main / other
+// stream), [2..5] = per-panel records of the single-GPU driver (outer-block parity x inner panel).
+static int laswp_slots(mmr_ctx* ctx, LaswpPerm** out) {
+  if (!ctx->laswp_buf) MMR_CUDA(cudaMalloc(&ctx->laswp_buf, 6 * sizeof(LaswpPerm)));
+  *out = (LaswpPerm*)ctx->laswp_buf;
+  return 0;
+}
+
+// Turns the interchanges ipiv[k0..k1) into the permutation record `slot` (0..5).
+int mmr_lu_laswp_prepare(mmr_ctx* ctx, cudaStream_t strm, const int* d_ipiv, int k0, int k1, int slot) {
+  LaswpPerm* perms;
+  int rc = laswp_slots(ctx, &perms);
+  if (rc) return rc;
+  lu_laswp_prepare_kernel<<<1, 32, 0, strm>>>(d_ipiv, k0, k1 - k0, perms + slot);
+  MMR_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+// Applies record slot0 and then (slot1 >= 0) slot1 to the local columns [col_begin, col_end).
+int mmr_lu_laswp_apply(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int col_begin, int col_end, int slot0,
+                       int slot1) {
+  if (col_end <= col_begin) return 0;
+  LaswpPerm* perms;
+  int rc = laswp_slots(ctx, &perms);
+  if (rc) return rc;
+  const int warps = 8;
+  lu_laswp_apply_kernel<<<(unsigned)ceil_div64(col_end - col_begin, warps), warps * 32, 0, strm>>>(
+      A, ld, col_begin, col_end, perms + slot0, slot1 >= 0 ? perms + slot1 : nullptr);
+  MMR_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+// Applies the interchanges ipiv[k0..k1) to local columns [col_begin, col_end) (prepare + apply;
+// one scratch record per stream: calls on one stream are ordered).
 int mmr_lu_laswp(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int k0, int k1, int col_begin, int col_end,
                  const int* d_ipiv) {
   if (col_end <= col_begin || k1 <= k0) return 0;
-  const int threads = 128;
-  lu_laswp_kernel<<<(unsigned)ceil_div64(col_end - col_begin, threads), threads, (k1 - k0) * sizeof(int),
-                    strm>>>(A, ld, k0, k1, col_begin, col_end, d_ipiv);
-  MMR_CHECK_LAUNCH(ctx);
-  return 0;
+  const int slot = (strm == ctx->stream) ? 0 : 1;
+  int rc = mmr_lu_laswp_prepare(ctx, strm, d_ipiv, k0, k1, slot);
+  if (rc) return rc;
+  return mmr_lu_laswp_apply(ctx, strm, A, ld, col_begin, col_end, slot, -1);
 }
 
 int mmr_lu_trsm(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, int nb, double* B, int64_t ldb, int ncols) {
@@ -1054,6 +1462,12 @@ int mmr_lu_trtri(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, 
   return mmr_lu_trsm(ctx, strm, L, ldl, nb, X, nb, nb);
 }
 
+// Single-GPU driver.  Two-level blocking: panels of NB = 128 columns are factored in pairs (an
+// "outer block" of OB = 256 columns), and the trailing matrix receives ONE rank-256 DMMA update per
+// outer block instead of two rank-128 updates: half the C read-modify-write traffic and half the
+// per-tile prologue/epilogue (measured on B200, m = n = 12288: 29.7 TF at k = 128, 32.3 TF at
+// k = 256).  The 256 x 256 unit-lower solve for U12 is done in two 128-row steps with the two
+// inverted diagonal blocks.
 extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld, int32_t* d_ipiv,
                              int* info_out) {
   MMR_ARG(ctx != nullptr, "ctx is NULL");
@@ -1064,80 +1478,134 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   MMR_ARG(d_Q && d_ipiv, "NULL matrix/pivot pointer");
   DeviceGuard g(ctx->device);
   const int N = (int)N64;
+  static int outer_mult = -1;
+  if (outer_mult < 0) {
+    const char* e = getenv("MMR_LU_OUTER");  // 1: rank-128 updates (one panel per outer block), 2: rank-256
+    outer_mult = (e && e[0] == '1') ? 1 : 2;
+  }
+  const int OB = outer_mult * NB;
+  static int spec_default = -1;
+  if (spec_default < 0) {
+    const char* e = getenv("MMR_LU_SPEC");  // 0: always the pivoting strip kernels
+    spec_default = (e && e[0] == '0') ? 0 : 1;
+  }
+  bool spec_on = spec_default != 0;  // switched off for the rest of this factorization after a failed check
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 2 * sizeof(double) * NB * NB);
+  const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
+  const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256 * 256) : 0;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 4 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 256);
   if (rc) return rc;
   int* d_info = (int*)ctx->ws;
   void* scratch = (char*)ctx->ws + 256;
-  double* Linv[2] = {(double*)((char*)ctx->ws + 256 + scratch_bytes),
-                     (double*)((char*)ctx->ws + 256 + scratch_bytes) + NB * NB};
+  double* Lbuf = (double*)((char*)ctx->ws + 256 + scratch_bytes);
+  void* d_spec = (char*)Lbuf + 4 * sizeof(double) * NB * NB;
+  double* Sbuf = (double*)((char*)d_spec + spec_bytes);
+  // inverse of the unit-lower diagonal block of inner panel `inner` of the outer block at kb
+  auto Linv = [&](int kb, int inner) { return Lbuf + (size_t)((((kb / OB) & 1) << 1) + inner) * NB * NB; };
   MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
   double* A = d_Q;
   cudaStream_t main_s = ctx->stream;
   cudaStream_t side_s = ctx->side;
-  // trailing update of the column range [cb, ce) by panel kb (swaps, U12 = L11^-1 A12, A22 -= L21 U12)
-  auto update_cols = [&](int kb, int nb, int cb, int ce) -> int {
+  // interchange records: slot(kb, inner), prepared once per panel on the stream that factored it
+  auto pslot = [&](int kb, int inner) { return 2 + ((((kb / OB) & 1) << 1) + inner); };
+  auto laswp = [&](cudaStream_t s, int cb, int ce, int slot0, int slot1) -> int {
     if (ce <= cb) return 0;
-    int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, main_s);
-    int r = mmr_lu_laswp(ctx, main_s, A, ld, kb, kb + nb, cb, ce, d_ipiv);
-    if (r) return r;
-    mmr_prof_end(ctx, ps, 32.0 * nb * (double)(ce - cb), main_s);
-    // U12 = L11^-1 A12 as an in-place DMMA GEMM (one m-tile: each CTA reads its whole B tile
-    // into shared memory before it stores, and no other CTA touches those columns)
-    ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, main_s);
-    r = mmr_dgemm_launch(ctx, main_s, nb, ce - cb, nb, 1.0, Linv[(kb / NB) & 1], nb, A + (int64_t)cb * ld + kb, ld,
-                         0.0, A + (int64_t)cb * ld + kb, ld);
-    if (r) return r;
-    mmr_prof_end(ctx, ps, 2.0 * nb * nb * (ce - cb), main_s);
-    const int mrows = N - (kb + nb);
-    ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, main_s);
-    r = mmr_dgemm_launch(ctx, main_s, mrows, ce - cb, nb, -1.0, A + (int64_t)kb * ld + (kb + nb), ld,
-                         A + (int64_t)cb * ld + kb, ld, 1.0, A + (int64_t)cb * ld + (kb + nb), ld);
-    if (r) return r;
-    mmr_prof_end(ctx, ps, 2.0 * mrows * (double)(ce - cb) * nb, main_s);
-    return 0;
+    const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, s);
+    const int r = mmr_lu_laswp_apply(ctx, s, A, ld, cb, ce, slot0, slot1);
+    mmr_prof_end(ctx, ps, 32.0 * NB * (double)(ce - cb), s);
+    return r;
   };
-  // Look-ahead (depth 1): as soon as the columns of panel k+1 have received the update of panel
-  // k, panel k+1 is factored on the high-priority side stream while the main stream applies the
-  // rest of update k.  The two touch disjoint column ranges.
-  const bool lookahead = ctx->lookahead;
-  rc = mmr_lu_panel(ctx, main_s, A, ld, N, 0, min(NB, N), d_ipiv, d_info, scratch);
-  if (rc) return rc;
-  rc = mmr_lu_trtri(ctx, main_s, A, ld, min(NB, N), Linv[0]);
-  if (rc) return rc;
-  for (int kb = 0; kb < N; kb += NB) {
-    const int nb = min(NB, N - kb);
-    const int next = kb + nb;
-    // left swaps of panel kb (columns already factored)
-    {
-      const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, main_s);
-      rc = mmr_lu_laswp(ctx, main_s, A, ld, kb, kb + nb, 0, kb, d_ipiv);
-      if (rc) return rc;
-      mmr_prof_end(ctx, ps, 32.0 * nb * (double)kb, main_s);
+  // B <- Linv * B in place on rows [r0, r0+nb) of columns [cb, ce): one m-tile, so each CTA has its
+  // whole B tile in shared memory before it stores and no other CTA touches those columns.
+  auto trsm = [&](cudaStream_t s, const double* Li, int r0, int nb, int cb, int ce) -> int {
+    const int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, s);
+    const int r = mmr_dgemm_launch(ctx, s, nb, ce - cb, nb, 1.0, Li, nb, A + (int64_t)cb * ld + r0, ld, 0.0,
+                                   A + (int64_t)cb * ld + r0, ld);
+    mmr_prof_end(ctx, ps, 2.0 * nb * nb * (double)(ce - cb), s);
+    return r;
+  };
+  // A[r0:r1, cb:ce] -= A[r0:r1, k0:k0+k] * A[k0:k0+k, cb:ce]
+  auto gemm = [&](cudaStream_t s, int kind, int r0, int r1, int k0, int k, int cb, int ce) -> int {
+    if (r1 <= r0 || ce <= cb) return 0;
+    const int ps = mmr_prof_begin(ctx, kind, s);
+    const int r = mmr_dgemm_launch(ctx, s, r1 - r0, ce - cb, k, -1.0, A + (int64_t)k0 * ld + r0, ld,
+                                   A + (int64_t)cb * ld + k0, ld, 1.0, A + (int64_t)cb * ld + r0, ld);
+    mmr_prof_end(ctx, ps, 2.0 * (r1 - r0) * (double)(ce - cb) * k, s);
+    return r;
+  };
+  // panel [kb, kb+nb) and the inverse of its unit-lower diagonal block: speculative (diagonal
+  // pivots, verified; blocks the host until the check is known) or the pivoting strip kernels
+  auto panel = [&](cudaStream_t s, int kb, int nb, double* Linv_out) -> int {
+    if (spec_on) {
+      int ok = 0;
+      const int r = mmr_lu_panel_spec(ctx, s, A, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, &ok);
+      if (r || ok) return r;
+      spec_on = false;
     }
+    const int r = mmr_lu_panel(ctx, s, A, ld, N, kb, nb, d_ipiv, d_info, scratch);
+    if (r) return r;
+    return mmr_lu_trtri(ctx, s, A + (int64_t)kb * ld + kb, ld, nb, Linv_out);
+  };
+  // factor the outer block [kb, kb+ob): panel 0, its update of panel 1's columns, panel 1
+  auto factor_outer = [&](cudaStream_t s, int kb, int ob) -> int {
+    const int nb0 = min(NB, ob);
+    int r = panel(s, kb, nb0, Linv(kb, 0));
+    if (r) return r;
+    r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, kb, kb + nb0, pslot(kb, 0));
+    if (r || ob <= NB) return r;
+    const int k1 = kb + NB, nb1 = ob - NB;
+    if ((r = laswp(s, k1, k1 + nb1, pslot(kb, 0), -1))) return r;
+    if ((r = trsm(s, Linv(kb, 0), kb, NB, k1, k1 + nb1))) return r;
+    if ((r = gemm(s, MMR_PROF_PANEL_GEMM, k1, N, kb, NB, k1, k1 + nb1))) return r;
+    if ((r = panel(s, k1, nb1, Linv(kb, 1)))) return r;
+    if ((r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, k1, k1 + nb1, pslot(kb, 1)))) return r;
+    return laswp(s, kb, k1, pslot(kb, 1), -1);  // panel 1's interchanges on panel 0's columns
+  };
+  // trailing update of the column range [cb, ce) by the outer block [kb, kb+ob)
+  auto update_cols = [&](int kb, int ob, int cb, int ce) -> int {
+    if (ce <= cb) return 0;
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
+    int r = laswp(main_s, cb, ce, pslot(kb, 0), nb1 > 0 ? pslot(kb, 1) : -1);
+    if (r) return r;
+    if ((r = trsm(main_s, Linv(kb, 0), kb, nb0, cb, ce))) return r;
+    if (nb1 > 0) {
+      if ((r = gemm(main_s, MMR_PROF_TRSM, kb + nb0, kb + ob, kb, nb0, cb, ce))) return r;
+      if ((r = trsm(main_s, Linv(kb, 1), kb + nb0, nb1, cb, ce))) return r;
+    }
+    return gemm(main_s, MMR_PROF_GEMM, kb + ob, N, kb, ob, cb, ce);
+  };
+  // Look-ahead (depth 1): as soon as the columns of outer block k+1 have received the update of
+  // block k, block k+1 is factored on the high-priority side stream while the main stream applies
+  // the rest of update k.  The two touch disjoint column ranges.
+  const bool lookahead = ctx->lookahead;
+  rc = factor_outer(main_s, 0, min(OB, N));
+  if (rc) return rc;
+  for (int kb = 0; kb < N; kb += OB) {
+    const int ob = min(OB, N - kb);
+    const int next = kb + ob;
+    // interchanges of this outer block on the columns already factored
+    if ((rc = laswp(main_s, 0, kb, pslot(kb, 0), ob > NB ? pslot(kb, 1) : -1))) return rc;
     if (next >= N) break;
-    const int nb2 = min(NB, N - next);
-    rc = update_cols(kb, nb, next, next + nb2);
+    const int ob2 = min(OB, N - next);
+    rc = update_cols(kb, ob, next, next + ob2);
     if (rc) return rc;
     if (lookahead) {
+      // the main stream's work is enqueued first: the speculative panels make the host wait for
+      // the side stream, and the device must not run out of queued work meanwhile
       MMR_CUDA(cudaEventRecord(ctx->ev[0], main_s));
-      MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
-      rc = mmr_lu_panel(ctx, side_s, A, ld, N, next, nb2, d_ipiv, d_info, scratch);
+      rc = update_cols(kb, ob, next + ob2, N);
       if (rc) return rc;
-      rc = mmr_lu_trtri(ctx, side_s, A + (int64_t)next * ld + next, ld, nb2, Linv[(next / NB) & 1]);
+      MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
+      rc = factor_outer(side_s, next, ob2);
       if (rc) return rc;
       MMR_CUDA(cudaEventRecord(ctx->ev[1], side_s));
-      rc = update_cols(kb, nb, next + nb2, N);
-      if (rc) return rc;
       MMR_CUDA(cudaStreamWaitEvent(main_s, ctx->ev[1], 0));
     } else {
-      rc = update_cols(kb, nb, next + nb2, N);
+      rc = update_cols(kb, ob, next + ob2, N);
       if (rc) return rc;
-      rc = mmr_lu_panel(ctx, main_s, A, ld, N, next, nb2, d_ipiv, d_info, scratch);
-      if (rc) return rc;
-      rc = mmr_lu_trtri(ctx, main_s, A + (int64_t)next * ld + next, ld, nb2, Linv[(next / NB) & 1]);
+      rc = factor_outer(main_s, next, ob2);
       if (rc) return rc;
     }
   }
@@ -1160,7 +1628,7 @@ int mmr_lu_tri_solves(mmr_ctx* ctx, int N, const double* A, int64_t ld, double* 
   }
   for (int k0 = 0; k0 < N; k0 += SB) {
     const int k1 = min(N, k0 + SB);
-    lu_diag_solve_kernel<true><<<1, SB, smem, ctx->stream>>>(A, ld, k0, k1, d_b);
+    lu_diag_solve_kernel<true><<<1, DIAG_THREADS, smem, ctx->stream>>>(A, ld, k0, k1, N, d_b);
     MMR_CHECK_LAUNCH(ctx);
     if (k1 < N) {
       lu_gemv_t_kernel<<<(unsigned)ceil_div64((int64_t)(N - k1) * 32, 256), 256, 0, ctx->stream>>>(
@@ -1172,7 +1640,7 @@ int mmr_lu_tri_solves(mmr_ctx* ctx, int N, const double* A, int64_t ld, double* 
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int k0 = blk * SB;
     const int k1 = min(N, k0 + SB);
-    lu_diag_solve_kernel<false><<<1, SB, smem, ctx->stream>>>(A, ld, k0, k1, d_b);
+    lu_diag_solve_kernel<false><<<1, DIAG_THREADS, smem, ctx->stream>>>(A, ld, k0, k1, N, d_b);
     MMR_CHECK_LAUNCH(ctx);
     if (k0 > 0) {
       lu_gemv_t_kernel<<<(unsigned)ceil_div64((int64_t)k0 * 32, 256), 256, 0, ctx->stream>>>(
@@ -1399,7 +1867,7 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
         lu_gemv_t_block_kernel<<<nb, 256, 0, st>>>(Ash, ld, 0, kb, kb, d_b, d_b);
         MMR_CHECK_LAUNCH(ctx);
       }
-      lu_diag_solve_kernel<true><<<1, SB, diag_smem, st>>>(Ash, ld, kb, kb + nb, d_b);
+      lu_diag_solve_kernel<true><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb, kb + nb, 0, d_b);
       MMR_CHECK_LAUNCH(ctx);
     }
     if (R > 1) {
@@ -1415,7 +1883,7 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
         lu_gemv_t_block_kernel<<<nb, 256, 0, st>>>(Ash, ld, kb + nb, N, kb, d_b, d_b);
         MMR_CHECK_LAUNCH(ctx);
       }
-      lu_diag_solve_kernel<false><<<1, SB, diag_smem, st>>>(Ash, ld, kb, kb + nb, d_b);
+      lu_diag_solve_kernel<false><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb, kb + nb, 0, d_b);
       MMR_CHECK_LAUNCH(ctx);
     }
     if (R > 1) {

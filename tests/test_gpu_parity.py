@@ -307,6 +307,40 @@ def test_lu_solve_random_dense_vs_numpy(ctx, N):
     assert np.all(p >= np.arange(N)) and np.all(p < N)
 
 
+@pytest.mark.parametrize(("N", "ndom"), [(300, 300), (777, 777), (900, 384), (1500, 130), (2049, 1100)])
+def test_lu_speculative_panels_then_pivoting(ctx, N, ndom):
+    """The first `ndom` columns of Q^T are diagonally dominant (the speculative diagonal-pivot panels
+    pass their |l| <= 1 check, pivots = identity there, as LAPACK would choose), the rest is a
+    general matrix that needs interchanges (falls back to the pivoting strip kernels)."""
+    rng = np.random.default_rng(N + ndom)
+    Q = rng.normal(size=(N, N))
+    Q[np.arange(ndom), np.arange(ndom)] += 8.0 * np.sqrt(N)
+    b = rng.normal(size=(N,))
+    ld = (N + 15) // 16 * 16
+    dQ = torch.zeros(N, ld, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    ipiv = torch.zeros(N, dtype=torch.int32, device=ctx.device)
+    assert ctx.lu_factor(dQ, ld, ipiv) == 0
+    dx = dev(ctx, b)
+    ctx.lu_solve(dQ, ld, ipiv, dx)
+    x = dx.cpu().numpy()
+    resid = np.linalg.norm(Q @ x - b) / (np.linalg.norm(Q) * np.linalg.norm(x))
+    assert resid < 1e-14, resid
+    p = ipiv.cpu().numpy()
+    nfull = (ndom // 128) * 128 if ndom < N else N  # panels that lie entirely in the dominant part
+    assert np.array_equal(p[:nfull], np.arange(nfull))
+    # packed factors reproduce Q^T = P L U
+    LU = dQ[:, :N].cpu().numpy().T  # column-major view A = Q^T
+    L = np.tril(LU, -1) + np.eye(N)
+    U = np.triu(LU)
+    PA = Q.T.copy()
+    for i in range(N):
+        if p[i] != i:
+            PA[[i, p[i]]] = PA[[p[i], i]]
+    assert np.abs(L @ U - PA).max() < 1e-11 * np.abs(Q).max() * np.sqrt(N)
+    assert np.abs(np.tril(LU, -1)).max() <= 1.0 + 1e-12
+
+
 def test_lu_reports_singular_matrix(ctx):
     N = 40
     Q = np.random.default_rng(0).normal(size=(N, N))
