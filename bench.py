@@ -35,6 +35,9 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("MMR_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 FLOP_PER_PAIR_ALIGNED = 2162.0  # SURVEY 8d convention (sqrt=20, log=50, atan2=65, add/mul=1)
 FLOP_PER_PAIR_ROTATED = 2288.0

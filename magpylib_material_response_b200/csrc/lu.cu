@@ -1033,75 +1033,109 @@ size_t mmr_lu_panel_scratch_bytes() { return 2 * 256 * sizeof(Cand) + (2 * 256 *
 // =======================================================================================
 namespace {
 
-// Thread (r, q) owns row r, columns [q*SEG, (q+1)*SEG) in registers.  Segment q lags q time steps
-// behind segment 0 so that one __syncthreads per step is enough: at time t it applies step
-// j = t - q using the multiplier column published by the pivot segment (ring lcol) and its part of
-// pivot row j (urow), which its thread r = j published at the end of the previous time step.
-// Inside its own pivot phase a segment rotates its registers by one per step (fused into the
-// update), so the current column is always v[0] and no dynamic register indexing is needed.
+// 1/a without the division slow path: MUFU.RCP64H seed (20 bits) + Newton steps (20 -> 40 -> 80 bits, a
+// third one absorbs the seed's worst case), straight-line so that it overlaps the independent DFMAs
+// around it (LAPACK's dgetf2 also scales by a reciprocal).
+__device__ __forceinline__ double fast_rcp(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  x = fma(x, fma(-a, x, 1.0), x);
+  x = fma(x, fma(-a, x, 1.0), x);
+  x = fma(x, fma(-a, x, 1.0), x);
+  return x;
+}
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// Thread (r, q) owns row r, columns [q*SEG, (q+1)*SEG) in registers.  The 128 steps run in NQ
+// phases of SEG steps; in phase p segment p is the pivot segment (its SEG steps are fully unrolled:
+// every register index is static, finished columns cost nothing), segments q > p apply each step
+// one barrier interval later (they need the multiplier column the pivot segment publishes), and
+// segments q < p only keep the barrier count.  One CTA barrier per step.  Pivot row j+1 is
+// published by its owner thread right after it has applied step j; the reciprocal of the next
+// pivot is computed first so that it overlaps the rest of the update.
 template <int SEG>
 __global__ void __launch_bounds__(128 * (128 / SEG), 1)
     lu_diag_nopiv_kernel(const double* __restrict__ A, int64_t ld, int kb, int nb, double* __restrict__ S,
                          int64_t lds, int* __restrict__ flag) {
   constexpr int NQ = 128 / SEG;
   __shared__ __align__(16) double urow[NQ][2][SEG];
-  __shared__ double lcol[NQ][128];
+  __shared__ __align__(16) double lcol[2][128];
+  __shared__ double s_rinv[2];
   __shared__ int s_bad;
   const int tid = threadIdx.x, r = tid & 127, q = tid >> 7;
-  const int warp_rmax = (r | 31);  // largest row of my warp
   double v[SEG];
 #pragma unroll
   for (int c = 0; c < SEG; ++c) {
     const int gc = q * SEG + c;
     v[c] = (r < nb && gc < nb) ? A[(int64_t)(kb + gc) * ld + kb + r] : ((r == gc) ? 1.0 : 0.0);
   }
-  if (tid == 0) s_bad = 0;
+  if (tid == 0) {
+    s_bad = 0;
+    s_rinv[0] = fast_rcp(v[0]);
+  }
   if (r == 0) {
 #pragma unroll
     for (int c = 0; c < SEG; ++c) urow[q][0][c] = v[c];
   }
-  __syncthreads();
+  cta_bar();
   bool bad = false;
 #pragma unroll 1
-  for (int t = 0; t < 128 + NQ - 1; ++t) {
-    const int j = t - q;  // warp-uniform
-    if (j >= 0 && j < 128) {
-      const int p = j / SEG;
-      const double* u = urow[q][j & 1];
-      if (q == p) {
-        const double piv = u[0];
-        const double rinv = 1.0 / piv;
-        const bool act = r > j;
-        const double l = act ? v[0] * rinv : 0.0;
-        if (piv == 0.0 || (act && !(fabs(l) <= 1.0))) bad = true;
-        const double keep = act ? l : v[0];
-        if (NQ > 1) lcol[j % NQ][r] = l;
-        if (warp_rmax > j) {
+  for (int p = 0; p < NQ; ++p) {
+    if (q == p) {
 #pragma unroll
-          for (int c = 1; c < SEG; ++c) v[c - 1] = v[c] - l * u[c];
-        } else {  // every row of this warp is already a row of U: rotation only
+      for (int i = 0; i <= SEG; ++i) {
+        if (i < SEG) {
+          const int j = p * SEG + i;
+          const double* u = urow[q][j & 1];
+          const double rinv = s_rinv[j & 1];
+          const bool act = r > j;
+          const double l = act ? v[i] * rinv : 0.0;
+          if (u[i] == 0.0 || (act && !(fabs(l) <= 1.0))) bad = true;
+          if (act) v[i] = l;
+          lcol[j & 1][r] = l;
+          if (i + 1 < SEG) {
+            v[i + 1] -= l * u[i + 1];
+            const double nrinv = fast_rcp(v[i + 1]);
 #pragma unroll
-          for (int c = 1; c < SEG; ++c) v[c - 1] = v[c];
+            for (int c = i + 2; c < SEG; ++c) v[c] -= l * u[c];
+            if (r == j + 1) {
+              s_rinv[(j + 1) & 1] = nrinv;
+              double* un = urow[q][(j + 1) & 1];
+#pragma unroll
+              for (int c = i + 1; c < SEG; ++c) un[c] = v[c];
+            }
+          }
         }
-        v[SEG - 1] = keep;
-      } else if (q > p && warp_rmax > j) {
-        const double l = lcol[j % NQ][r];
-#pragma unroll
-        for (int c = 0; c < SEG; ++c) v[c] -= l * u[c];
+        cta_bar();
       }
-      // publish my part of pivot row j+1 for my segment's next step
-      const int jn = j + 1;
-      if (r == jn && jn < 128 && q >= jn / SEG) {
-        const int valid = (q == jn / SEG) ? SEG - (jn - q * SEG) : SEG;  // rotated positions still to update
-        double* un = urow[q][jn & 1];
+    } else if (q > p) {
 #pragma unroll
-        for (int c = 0; c < SEG; ++c) un[c] = (c < valid) ? v[c] : 0.0;
+      for (int i = 0; i <= SEG; ++i) {
+        if (i >= 1) {
+          const int j = p * SEG + i - 1;
+          const double* u = urow[q][j & 1];
+          const double l = lcol[j & 1][r];
+          v[0] -= l * u[0];
+          double nrinv = 0.0;
+          if (i == SEG && q == p + 1) nrinv = fast_rcp(v[0]);  // my segment is the next pivot segment
+#pragma unroll
+          for (int c = 1; c < SEG; ++c) v[c] -= l * u[c];
+          if (r == j + 1) {
+            if (i == SEG && q == p + 1) s_rinv[(j + 1) & 1] = nrinv;
+            double* un = urow[q][(j + 1) & 1];
+#pragma unroll
+            for (int c = 0; c < SEG; ++c) un[c] = v[c];
+          }
+        }
+        cta_bar();
       }
+    } else {
+#pragma unroll 1
+      for (int i = 0; i <= SEG; ++i) cta_bar();
     }
-    __syncthreads();
   }
   if (bad) s_bad = 1;
-  __syncthreads();
+  cta_bar();
   if (tid == 0) *flag = s_bad;
 #pragma unroll
   for (int c = 0; c < SEG; ++c) {
@@ -1125,23 +1159,37 @@ __global__ void __launch_bounds__(256)
   const int tid = threadIdx.x;
   const int cb = blockIdx.x * TINV_COLS;
   const int nc = min(TINV_COLS, nb - cb);
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int r = e % nb, c = e / nb;
-    double val = 0.0;
-    if (upper) {
-      // lower-triangular T = U^T: T(r, c) = U(c, r) = S[r*lds + c]; read coalesced along the fast index
-      const int rr = e / nb, cc = e % nb;  // (row rr, col cc) of T with cc fastest
-      if (rr >= cc) Ls[cc * (nb + 1) + rr] = S[(int64_t)rr * lds + cc];
-      continue;
+  // lower-triangular T in Ls[c*(nb+1) + r] (r >= c).  L: T(r, c) = S[c*lds + r] (unit diagonal);
+  // U: T = U^T, T(r, c) = U(c, r) = S[r*lds + c].  `f` is the fast (contiguous) index of S.
+  for (int base = 0; base < nb * nb; base += 8 * 256) {
+    double tmp[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = base + tid + k * 256;
+      const int f = e % nb, g = e / nb;  // S[g*lds + f]
+      const bool need = (e < nb * nb) && (upper ? (g >= f) : (f > g));
+      tmp[k] = need ? __ldg(S + (int64_t)g * lds + f) : 1.0;  // L: the unit diagonal
     }
-    if (r > c) val = S[(int64_t)c * lds + r];
-    else if (r == c) val = 1.0;
-    if (r >= c) Ls[c * (nb + 1) + r] = val;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = base + tid + k * 256;
+      const int f = e % nb, g = e / nb;
+      if (e < nb * nb) {
+        if (upper) {
+          if (g >= f) Ls[f * (nb + 1) + g] = tmp[k];
+        } else if (f >= g) {
+          Ls[g * (nb + 1) + f] = tmp[k];
+        }
+      }
+    }
   }
   for (int e = tid; e < nc * nb; e += blockDim.x) {
     const int r = e % nb, c = e / nb;
     Bs[c * (nb + 1) + r] = (r == cb + c) ? 1.0 : 0.0;
   }
+  __syncthreads();
+  __shared__ double s_rd[NB];  // reciprocals of the diagonal: 16 dependent divisions per block step otherwise
+  if (tid < nb) s_rd[tid] = upper ? 1.0 / Ls[tid * (nb + 1) + tid] : 1.0;
   __syncthreads();
   constexpr int TB = 16;
   const int c = tid % TINV_COLS;
@@ -1158,7 +1206,7 @@ __global__ void __launch_bounds__(256)
         if (i < tb) {
 #pragma unroll
           for (int qq = 0; qq < i; ++qq) x[i] -= Ls[(t0 + qq) * (nb + 1) + t0 + i] * x[qq];
-          x[i] /= Ls[(t0 + i) * (nb + 1) + t0 + i];
+          x[i] *= s_rd[t0 + i];
         }
       }
 #pragma unroll
@@ -1738,7 +1786,7 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
   MMR_ARG(ctx != nullptr, "ctx is NULL");
   MMR_ARG(N64 >= 0 && N64 < (1LL << 31) && N64 % 3 == 0, "N out of range / not a multiple of 3");
   MMR_ARG(ld >= N64 && tgt_block >= 1 && nrows_local >= 0, "bad sizes");
-  MMR_ARG(3 * tgt_block <= NB, "distributed LU needs 3*tgt_block <= 128");
+  MMR_ARG(3 * tgt_block <= 2 * NB, "distributed LU needs 3*tgt_block <= 256");
   MMR_ARG(ctx->nranks == 1 || ctx->nccl_comm != nullptr, "communicator not initialised");
   if (info_out) *info_out = 0;
   if (N64 == 0) return 0;
@@ -1746,148 +1794,244 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
   DeviceGuard g(ctx->device);
   const int N = (int)N64;
   const int R = ctx->nranks, me = ctx->rank;
-  const int nbw = (int)(3 * tgt_block);
-  const int S = (int)ceil_div64(N, nbw);
+  const int obw = (int)(3 * tgt_block);  // outer block = ownership unit = up to two 128-column panels
+  const int S = (int)ceil_div64(N, obw);
   {
     int64_t mine = 0;
-    for (int s = me; s < S; s += R) mine += min(nbw, N - s * nbw);
+    for (int s = me; s < S; s += R) mine += min(obw, N - s * obw);
     MMR_ARG(mine == nrows_local, "nrows_local does not match the block-cyclic ownership of this rank");
   }
   const int ncols_local = (int)nrows_local;
   cudaStream_t st = ctx->stream;
+  cudaStream_t side = ctx->side;
+  static int spec_default = -1;
+  if (spec_default < 0) {
+    const char* e = getenv("MMR_LU_SPEC");
+    spec_default = (e && e[0] == '0') ? 0 : 1;
+  }
+  bool spec_on = spec_default != 0;
 
+  // workspace: [info | strip scratch | spec scratch | ipiv | 2 x broadcast record | spec panel | tmp]
+  // broadcast record of an outer block: header (L11^-1 of both panels, the block's pivots) + packed
+  // panel (m x ob, ld = m): ONE ncclBroadcast per outer block.
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
-  const size_t linv_bytes = sizeof(double) * NB * NB;
+  const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
   const size_t ipiv_bytes = ((sizeof(int) * (size_t)N + 255) / 256) * 256;
-  const size_t p_bytes = ((sizeof(double) * (size_t)N * nbw + 255) / 256) * 256;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes + 2 * p_bytes + sizeof(double) * (size_t)N + 512);
+  const size_t hdr_doubles = 2 * (size_t)NB * NB + NB;  // + 2*NB ints
+  const size_t rec_bytes = ((sizeof(double) * (hdr_doubles + (size_t)N * obw) + 255) / 256) * 256;
+  const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256) * 256 : 0;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + spec_bytes + ipiv_bytes + 2 * rec_bytes + sbuf_bytes +
+                                   sizeof(double) * (size_t)N + 512);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
   if (rc) return rc;
   char* base = (char*)ctx->ws;
   int* d_info = (int*)base;
   void* scratch = base + 256;
-  double* Linv2[2] = {(double*)(base + 256 + scratch_bytes), (double*)(base + 256 + scratch_bytes + linv_bytes)};
-  int* d_ipiv = (int*)(base + 256 + scratch_bytes + 2 * linv_bytes);
-  double* P2[2] = {(double*)(base + 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes),
-                   (double*)(base + 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes + p_bytes)};
-  double* d_tmp = (double*)(base + 256 + scratch_bytes + 2 * linv_bytes + ipiv_bytes + 2 * p_bytes);
+  void* d_spec = base + 256 + scratch_bytes;
+  int* d_ipiv = (int*)(base + 256 + scratch_bytes + spec_bytes);
+  double* rec[2] = {(double*)(base + 256 + scratch_bytes + spec_bytes + ipiv_bytes),
+                    (double*)(base + 256 + scratch_bytes + spec_bytes + ipiv_bytes + rec_bytes)};
+  double* Sbuf = (double*)(base + 256 + scratch_bytes + spec_bytes + ipiv_bytes + 2 * rec_bytes);
+  double* d_tmp = (double*)((char*)Sbuf + sbuf_bytes);
+  auto LinvOf = [&](int s, int inner) { return rec[s & 1] + (size_t)inner * NB * NB; };
+  auto IpivOf = [&](int s) { return (int*)(rec[s & 1] + 2 * (size_t)NB * NB); };
+  auto PanelOf = [&](int s) { return rec[s & 1] + hdr_doubles; };
+  auto pslot = [&](int s, int inner) { return 2 + (((s & 1) << 1) + inner); };
   MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+  MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
+  MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));  // the side stream starts after everything queued so far
   double* Al = d_Qlocal;
-  cudaStream_t side = ctx->side;
 
-  // factor global panel s (owned by this rank) on stream `strm`, invert its diagonal block and pack it
+  auto trsm = [&](cudaStream_t s_, const double* Li, int nb, double* Bp, int ncols) -> int {
+    const int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, s_);
+    const int r = mmr_dgemm_launch(ctx, s_, nb, ncols, nb, 1.0, Li, nb, Bp, ld, 0.0, Bp, ld);
+    mmr_prof_end(ctx, ps, 2.0 * nb * nb * (double)ncols, s_);
+    return r;
+  };
+  // panel of the owner's local storage `Ash` (global column c at Ash + c*ld) and its L11^-1
+  auto panel = [&](cudaStream_t s_, double* Ash, int kb, int nb, double* Linv_out) -> int {
+    if (spec_on) {
+      int ok = 0;
+      const int r = mmr_lu_panel_spec(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, &ok);
+      if (r || ok) return r;
+      spec_on = false;
+    }
+    const int r = mmr_lu_panel(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
+    if (r) return r;
+    return mmr_lu_trtri(ctx, s_, Ash + (int64_t)kb * ld + kb, ld, nb, Linv_out);
+  };
+  // factor outer block s (owned by this rank) on stream `strm` and fill its broadcast record
   auto factor_and_pack = [&](int s, cudaStream_t strm) -> int {
-    const int kb = s * nbw, nb = min(nbw, N - kb), m = N - kb;
-    double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;  // global column kb -> my local column
-    int r = mmr_lu_panel(ctx, strm, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
+    const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
+    double* Ash = Al + ((int64_t)(s / R) * obw - kb) * ld;  // global column kb -> my local column
+    int r = panel(strm, Ash, kb, nb0, LinvOf(s, 0));
     if (r) return r;
-    r = mmr_lu_trtri(ctx, strm, Ash + (int64_t)kb * ld + kb, ld, nb, Linv2[s & 1]);
-    if (r) return r;
-    MMR_CUDA(cudaMemcpy2DAsync(P2[s & 1], sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
-                               sizeof(double) * m, nb, cudaMemcpyDeviceToDevice, strm));
+    if (nb1 > 0) {
+      const int k1 = kb + nb0;
+      if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, kb, k1, k1, k1 + nb1, d_ipiv))) return r;
+      if ((r = trsm(strm, LinvOf(s, 0), nb0, Ash + (int64_t)k1 * ld + kb, nb1))) return r;
+      const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
+      r = mmr_dgemm_launch(ctx, strm, N - k1, nb1, nb0, -1.0, Ash + (int64_t)kb * ld + k1, ld,
+                           Ash + (int64_t)k1 * ld + kb, ld, 1.0, Ash + (int64_t)k1 * ld + k1, ld);
+      if (r) return r;
+      mmr_prof_end(ctx, pg, 2.0 * (N - k1) * (double)nb1 * nb0, strm);
+      if ((r = panel(strm, Ash, k1, nb1, LinvOf(s, 1)))) return r;
+      if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, k1, k1 + nb1, kb, k1, d_ipiv))) return r;
+    }
+    MMR_CUDA(cudaMemcpy2DAsync(PanelOf(s), sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
+                               sizeof(double) * m, ob, cudaMemcpyDeviceToDevice, strm));
+    MMR_CUDA(cudaMemcpyAsync(IpivOf(s), d_ipiv + kb, sizeof(int) * ob, cudaMemcpyDeviceToDevice, strm));
     return 0;
   };
-  // apply panel s (pivots, U12 = L11^-1 A12, A22 -= L21 U12) to my local columns [c0, c1)
+  // apply outer block s (interchanges, U12 in two 128-row steps, one rank-ob update) to my local
+  // columns [c0, c1)
   auto update_local = [&](int s, int c0, int c1) -> int {
     if (c1 <= c0) return 0;
-    const int kb = s * nbw, nb = min(nbw, N - kb), m = N - kb;
-    const double* P = P2[s & 1];
-    int r = mmr_lu_laswp(ctx, st, Al, ld, kb, kb + nb, c0, c1, d_ipiv);
+    const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
+    const double* P = PanelOf(s);
+    double* B = Al + (int64_t)c0 * ld + kb;
+    int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
+    int r = mmr_lu_laswp_apply(ctx, st, Al, ld, c0, c1, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1);
     if (r) return r;
-    int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
-    r = mmr_dgemm_launch(ctx, st, nb, c1 - c0, nb, 1.0, Linv2[s & 1], nb, Al + (int64_t)c0 * ld + kb, ld, 0.0,
-                         Al + (int64_t)c0 * ld + kb, ld);
-    if (r) return r;
-    mmr_prof_end(ctx, ps, 2.0 * nb * nb * (c1 - c0), st);
-    if (m > nb) {
-      ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);
-      r = mmr_dgemm_launch(ctx, st, m - nb, c1 - c0, nb, -1.0, P + nb, m, Al + (int64_t)c0 * ld + kb, ld, 1.0,
-                           Al + (int64_t)c0 * ld + kb + nb, ld);
+    mmr_prof_end(ctx, ps, 32.0 * ob * (double)(c1 - c0), st);
+    if ((r = trsm(st, LinvOf(s, 0), nb0, B, c1 - c0))) return r;
+    if (nb1 > 0) {
+      ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
+      r = mmr_dgemm_launch(ctx, st, nb1, c1 - c0, nb0, -1.0, P + nb0, m, B, ld, 1.0, B + nb0, ld);
       if (r) return r;
-      mmr_prof_end(ctx, ps, 2.0 * (m - nb) * (double)(c1 - c0) * nb, st);
+      mmr_prof_end(ctx, ps, 2.0 * nb1 * (double)(c1 - c0) * nb0, st);
+      if ((r = trsm(st, LinvOf(s, 1), nb1, B + nb0, c1 - c0))) return r;
     }
+    if (m > ob) {
+      ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);
+      r = mmr_dgemm_launch(ctx, st, m - ob, c1 - c0, ob, -1.0, P + ob, m, B, ld, 1.0, B + ob, ld);
+      if (r) return r;
+      mmr_prof_end(ctx, ps, 2.0 * (m - ob) * (double)(c1 - c0) * ob, st);
+    }
+    return 0;
+  };
+  // broadcast record s on the side stream (overlaps the main stream's update of block s-1);
+  // ev[2 + (s&1)] marks its arrival
+  auto bcast_record = [&](int s) -> int {
+    const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
+    if (R > 1) {
+      const int r = mmr_comm_bcast_bytes(ctx, rec[s & 1], sizeof(double) * (hdr_doubles + (size_t)m * ob), s % R, side);
+      if (r) return r;
+    }
+    MMR_CUDA(cudaEventRecord(ctx->ev[2 + (s & 1)], side));
     return 0;
   };
 
   if (me == 0) {
-    rc = factor_and_pack(0, st);
+    rc = factor_and_pack(0, side);
     if (rc) return rc;
   }
+  rc = bcast_record(0);
+  if (rc) return rc;
   for (int s = 0; s < S; ++s) {
-    const int kb = s * nbw;
-    const int nb = min(nbw, N - kb);
-    const int m = N - kb;
-    const int owner = s % R;
-    if (R > 1) {
-      rc = mmr_comm_bcast_bytes(ctx, P2[s & 1], sizeof(double) * (size_t)m * nb, owner, st);
-      if (rc) return rc;
-      rc = mmr_comm_bcast_bytes(ctx, Linv2[s & 1], sizeof(double) * (size_t)nb * nb, owner, st);
-      if (rc) return rc;
-      rc = mmr_comm_bcast_bytes(ctx, d_ipiv + kb, sizeof(int) * (size_t)nb, owner, st);
+    const int kb = s * obw;
+    const int ob = min(obw, N - kb);
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
+    MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[2 + (s & 1)], 0));
+    // from here on the main stream no longer reads record s-1 = the buffer of record s+1
+    MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
+    MMR_CUDA(cudaMemcpyAsync(d_ipiv + kb, IpivOf(s), sizeof(int) * ob, cudaMemcpyDeviceToDevice, st));
+    rc = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb, kb + nb0, pslot(s, 0));
+    if (rc) return rc;
+    if (nb1 > 0) {
+      rc = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb + nb0, kb + ob, pslot(s, 1));
       if (rc) return rc;
     }
-    // my already-factored panels (global index < s): row swaps only
+    // my already-factored blocks (global index < s): interchanges only
     const int nleft = (s > me) ? ((s - 1 - me) / R + 1) : 0;
-    rc = mmr_lu_laswp(ctx, st, Al, ld, kb, kb + nb, 0, nleft * nbw, d_ipiv);
-    if (rc) return rc;
-    // my trailing panels (global index > s)
+    {
+      const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
+      rc = mmr_lu_laswp_apply(ctx, st, Al, ld, 0, nleft * obw, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1);
+      if (rc) return rc;
+      mmr_prof_end(ctx, ps, 32.0 * ob * (double)nleft * obw, st);
+    }
+    // my trailing blocks (global index > s)
     const int first_trail = (s >= me) ? ((s - me) / R + 1) : 0;
-    const int ct0 = first_trail * nbw, ct1 = ncols_local;
-    const bool own_next = (s + 1 < S) && ((s + 1) % R == me);
+    const int ct0 = first_trail * obw, ct1 = ncols_local;
+    const bool have_next = s + 1 < S;
+    const bool own_next = have_next && ((s + 1) % R == me);
     if (own_next) {
-      // look-ahead: bring my block of panel s+1 up to date first, factor it on the side stream while
-      // the main stream updates the rest of my trailing columns
-      const int nb1 = min(nbw, N - (s + 1) * nbw);
-      rc = update_local(s, ct0, ct0 + nb1);
+      // look-ahead: bring my next block up to date first, then factor it on the side stream while
+      // the main stream updates the rest of my trailing columns (enqueued first: the speculative
+      // panels make the host wait for the side stream)
+      const int ob1 = min(obw, N - (s + 1) * obw);
+      rc = update_local(s, ct0, ct0 + ob1);
       if (rc) return rc;
       MMR_CUDA(cudaEventRecord(ctx->ev[0], st));
+      rc = update_local(s, ct0 + ob1, ct1);
+      if (rc) return rc;
       MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
       rc = factor_and_pack(s + 1, side);
       if (rc) return rc;
-      MMR_CUDA(cudaEventRecord(ctx->ev[1], side));
-      rc = update_local(s, ct0 + nb1, ct1);
-      if (rc) return rc;
-      MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[1], 0));
     } else {
       rc = update_local(s, ct0, ct1);
       if (rc) return rc;
+      MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));
+    }
+    if (have_next) {
+      rc = bcast_record(s + 1);
+      if (rc) return rc;
     }
   }
+  // the solves below run on the main stream only, after everything on the side stream
+  MMR_CUDA(cudaEventRecord(ctx->ev[0], side));
+  MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[0], 0));
 
-  // ---- triangular solves, panel by panel --------------------------------------------------
+  // ---- triangular solves, block by block (each block in two <= 128-row steps) -----------------
   const size_t diag_smem = (size_t)SB * (SB + 1) * sizeof(double);
   MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
   MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
   for (int s = 0; s < S; ++s) {  // U^T w = b
-    const int kb = s * nbw, nb = min(nbw, N - kb), owner = s % R;
+    const int kb = s * obw, ob = min(obw, N - kb), owner = s % R;
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
     if (me == owner) {
-      const double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;
+      const double* Ash = Al + ((int64_t)(s / R) * obw - kb) * ld;
       if (kb > 0) {
-        lu_gemv_t_block_kernel<<<nb, 256, 0, st>>>(Ash, ld, 0, kb, kb, d_b, d_b);
+        lu_gemv_t_block_kernel<<<ob, 256, 0, st>>>(Ash, ld, 0, kb, kb, d_b, d_b);
         MMR_CHECK_LAUNCH(ctx);
       }
-      lu_diag_solve_kernel<true><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb, kb + nb, 0, d_b);
+      lu_diag_solve_kernel<true><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb, kb + nb0, 0, d_b);
       MMR_CHECK_LAUNCH(ctx);
+      if (nb1 > 0) {
+        lu_gemv_t_block_kernel<<<nb1, 256, 0, st>>>(Ash, ld, kb, kb + nb0, kb + nb0, d_b, d_b);
+        MMR_CHECK_LAUNCH(ctx);
+        lu_diag_solve_kernel<true><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb + nb0, kb + ob, 0, d_b);
+        MMR_CHECK_LAUNCH(ctx);
+      }
     }
     if (R > 1) {
-      rc = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * nb, owner, st);
+      rc = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * ob, owner, st);
       if (rc) return rc;
     }
   }
   for (int s = S - 1; s >= 0; --s) {  // L^T v = w
-    const int kb = s * nbw, nb = min(nbw, N - kb), owner = s % R;
+    const int kb = s * obw, ob = min(obw, N - kb), owner = s % R;
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
     if (me == owner) {
-      const double* Ash = Al + ((int64_t)(s / R) * nbw - kb) * ld;
-      if (kb + nb < N) {
-        lu_gemv_t_block_kernel<<<nb, 256, 0, st>>>(Ash, ld, kb + nb, N, kb, d_b, d_b);
+      const double* Ash = Al + ((int64_t)(s / R) * obw - kb) * ld;
+      if (kb + ob < N) {
+        lu_gemv_t_block_kernel<<<ob, 256, 0, st>>>(Ash, ld, kb + ob, N, kb, d_b, d_b);
         MMR_CHECK_LAUNCH(ctx);
       }
-      lu_diag_solve_kernel<false><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb, kb + nb, 0, d_b);
+      if (nb1 > 0) {
+        lu_diag_solve_kernel<false><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb + nb0, kb + ob, 0, d_b);
+        MMR_CHECK_LAUNCH(ctx);
+        lu_gemv_t_block_kernel<<<nb0, 256, 0, st>>>(Ash, ld, kb + nb0, kb + ob, kb, d_b, d_b);
+        MMR_CHECK_LAUNCH(ctx);
+      }
+      lu_diag_solve_kernel<false><<<1, DIAG_THREADS, diag_smem, st>>>(Ash, ld, kb, kb + nb0, 0, d_b);
       MMR_CHECK_LAUNCH(ctx);
     }
     if (R > 1) {
-      rc = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * nb, owner, st);
+      rc = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * ob, owner, st);
       if (rc) return rc;
     }
   }

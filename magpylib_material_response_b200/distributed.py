@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-DEFAULT_TGT_BLOCK = 40  # 3*40 = 120-wide panels (the distributed LU needs 3*tgt_block <= 128)
+DEFAULT_TGT_BLOCK = 80  # 3*80 = 240-row ownership blocks = two LU panels (128 + 112) and one rank-240 DMMA update; the distributed LU needs 3*tgt_block <= 256
 
 
 def owned_blocks(n_cells, tgt_block, nranks, rank):

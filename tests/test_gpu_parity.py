@@ -519,7 +519,7 @@ def test_config2prime_8000_cells_properties(ctx):
 # distributed entry points on ONE rank (the panel-by-panel code path; R > 1 is exercised by
 # tests/multi_gpu_parity.py under torchrun and by the gloo CPU tests)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize(("n", "tgt_block"), [(50, 8), (333, 40), (700, 42)])
+@pytest.mark.parametrize(("n", "tgt_block"), [(50, 8), (333, 40), (700, 42), (700, 80), (1000, 85), (640, 64)])
 def test_lu_solve_dist_single_rank_vs_numpy(ctx, n, tgt_block):
     N = 3 * n
     rng = np.random.default_rng(n)
