@@ -35,9 +35,16 @@ import numpy as np
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("MMR_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 behind Python's back
+# (NCCL prints its version banner there): point fd 1 at stderr for the whole process and keep a private
+# handle on the real stdout for the result line.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
 
 FLOP_PER_PAIR_ALIGNED = 2162.0  # SURVEY 8d convention (sqrt=20, log=50, atan2=65, add/mul=1)
 FLOP_PER_PAIR_ROTATED = 2288.0
@@ -195,7 +202,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "T-entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -369,12 +376,13 @@ def run_ours(args):
                 "entries_per_s": 9.0 * asm_pairs / (asm_ms * 1e-3) if asm_ms else None, "peak_src": peaks["fp64_src"]}
     if roof_asm["achieved"]:
         roof_asm["frac"] = roof_asm["achieved"] / roof_asm["peak"]
+    k_update = 256 if world == 1 else 3 * tgt_block  # rank of the trailing updates (two 128-column panels / one ownership block)
     if solver == "lu" and gemm_ms:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["fp64_dmma_tflops"],
-                    "traffic": traffic.get("dgemm_nn", {}).get("ratio", 0) * (gemm_flops / 16.0) / gemm_cnt or None,
-                    "traffic_src": "C read+write bytes (= flops/16 at k=128) x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
+                    "traffic": traffic.get("dgemm_nn", {}).get("ratio", 0) * (gemm_flops * 8.0 / k_update) / gemm_cnt or None,
+                    "traffic_src": f"C read+write bytes (16 B per C element = flops*8/k, rank-{k_update} updates) x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
                     "kernel": "dgemm_nn_fast_kernel (LU trailing update, DMMA.8x8x4)",
                     "launches": gemm_cnt, "ms_per_launch": gemm_ms / gemm_cnt,
                     "peak_src": "FP64 DMMA peak " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry"}
@@ -413,7 +421,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(name)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

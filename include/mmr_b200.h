@@ -16,6 +16,7 @@
  *                                                                       or mmr_gmres
  *   collection.getB(observers) of the solved cells                      mmr_field
  *       (tests/test_isotropic_anisotropic.py:23, magpylib call)
+ *   magpy.getB(currents_list, pos, sumup=True)    demag.py:456-463      mmr_field_currents
  *
  * Conventions
  *   - All floating point is FP64.  All pointers named d_* are DEVICE pointers owned by the
@@ -167,6 +168,18 @@ int mmr_matvec(mmr_ctx* ctx, int64_t nrows, int64_t ncols, const double* d_Q, in
 int mmr_field(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
               const double* d_dim, const double* d_pol, int64_t m, const double* d_obs,
               int field, double* d_out);
+
+/* ---- field of current sources at observers (magpy.getB(currents_list, pos, sumup=True),
+ *      demag.py:456-463: the current-source term of the right-hand side) ---- */
+/* d_seg : [nseg][7]  straight segments of current.Polyline objects in the GLOBAL frame:
+ *                    (p1x, p1y, p1z, p2x, p2y, p2z, current in A)
+ * d_loop: [nloop][9] current.Circle objects: (centre xyz, orientation quaternion x,y,z,w
+ *                    scalar-last, diameter in m, current in A); the loop lies in its local xy plane
+ * d_out : [m][3] global-frame B (tesla) or H (A/m), summed over all elements.  Observers on a
+ *         conductor get no contribution from it (magpylib convention). */
+int mmr_field_currents(mmr_ctx* ctx, int64_t m, const double* d_obs, int64_t nseg,
+                       const double* d_seg, int64_t nloop, const double* d_loop, int field,
+                       double* d_out);
 
 /* ---- multi-GPU (one process per GPU; NCCL communicator owned by the context) ------------ */
 /* rank 0 calls mmr_nccl_unique_id, the 128-byte id is shipped to the other ranks by the host

@@ -8,9 +8,10 @@ Compute runs in hand-written CUDA for sm_100a behind the C ABI in include/mmr_b2
 from __future__ import annotations
 
 from . import demag, meshing
-from ._compat import HAVE_MAGPYLIB, BaseCurrent, BaseMagnet, Collection, Cuboid, Sensor, mu_0
+from ._compat import HAVE_MAGPYLIB, BaseCurrent, BaseMagnet, Circle, Collection, Cuboid, Polyline, Sensor, mu_0
 from .demag import apply_demag, demag_tensor, get_H_ext, get_susceptibilities
-from .meshing import mesh_Cuboid
+from .meshing import mesh_all, mesh_Cuboid, slice_Cuboid
+from .serialization import from_json, to_json
 
 __version__ = "0.1.0"
 
@@ -18,16 +19,22 @@ __all__ = [
     "HAVE_MAGPYLIB",
     "BaseCurrent",
     "BaseMagnet",
+    "Circle",
     "Collection",
     "Cuboid",
+    "Polyline",
     "Sensor",
     "__version__",
     "apply_demag",
     "demag",
     "demag_tensor",
+    "from_json",
     "get_H_ext",
     "get_susceptibilities",
     "mesh_Cuboid",
+    "mesh_all",
     "meshing",
     "mu_0",
+    "slice_Cuboid",
+    "to_json",
 ]

@@ -95,6 +95,11 @@ _SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
          ctypes.c_int64, _c_double_p, ctypes.c_int, _c_double_p],
     ),
+    "mmr_field_currents": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p, ctypes.c_int64,
+         _c_double_p, ctypes.c_int, _c_double_p],
+    ),
     "mmr_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "mmr_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "mmr_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
@@ -307,6 +312,14 @@ class Context:
     def field(self, pos, quat, dim, pol, obs, out, field=FIELD_B):
         _check(self.lib, self.lib.mmr_field(self.handle, pos.shape[0], _ptr(pos), _ptr(quat), _ptr(dim),
                                             _ptr(pol), obs.shape[0], _ptr(obs), field, _ptr(out)))
+
+    def field_currents(self, obs, seg, loop, out, field=FIELD_B):
+        """seg: (nseg,7) device tensor or None; loop: (nloop,9) device tensor or None."""
+        nseg = 0 if seg is None else seg.shape[0]
+        nloop = 0 if loop is None else loop.shape[0]
+        _check(self.lib, self.lib.mmr_field_currents(self.handle, obs.shape[0], _ptr(obs), nseg,
+                                                     _ptr(seg) if nseg else None, nloop,
+                                                     _ptr(loop) if nloop else None, field, _ptr(out)))
 
     # ---- multi-GPU -------------------------------------------------------------------
     def comm_init_from_torch(self):

@@ -496,17 +496,19 @@ def apply_demag(
             _require_cuboids(magnets_list, "filter_distance")
         elif pairs_matching:
             _require_cuboids(magnets_list, "Pairs matching")
-        if currents_list:
-            msg = (
-                "Current sources are not evaluated by the B200 path yet (demag.py:456-463 needs "
-                "magpylib's current-loop fields); remove them or add their field as H_ext"
-            )
-            raise NotImplementedError(msg)
         if n == 0:
             return (collection if not inplace else None) if not return_info else (collection, info)
         _check_native_cells(magnets_list)
 
         pos, quat, dim = _cell_geometry(magnets_list)
+        if currents_list:
+            # demag.py:456-463: pol_total += S . getB(currents, cell positions), fields from the CUDA
+            # current-source kernel (mmr_field_currents)
+            from .field import current_field
+
+            with timelog("Add current sources contributions", min_log_time=min_log_time):
+                cell_pos = np.array([src.position for src in magnets_list], dtype=float).reshape(n, 3)
+                pol_global = pol_global + chi * current_field("B", currents_list, cell_pos, device=device)
         pol_new, solve_info = solve_cells_global(
             pos, quat, dim, pol_global, chi, H_ext, pairs_matching=pairs_matching, max_dist=max_dist,
             split=split, solver=solver, tol=tol, device=device, min_log_time=min_log_time,

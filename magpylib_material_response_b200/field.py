@@ -1,7 +1,8 @@
-"""``getB`` / ``getH`` of cuboid cells at observers through the CUDA field kernel
-(``mmr_field``) -- stands in for the magpylib call the reference's tests make after the
-solve (/root/reference/tests/test_isotropic_anisotropic.py:23).
-Cuboid magnets only; no CPU fallback.
+"""``getB`` / ``getH`` at observers through the CUDA field kernels -- stands in for the magpylib
+calls the reference makes around the solve: ``collection.getB(observers)`` of the solved cells
+(/root/reference/tests/test_isotropic_anisotropic.py:23; ``mmr_field``) and
+``magpy.getB(currents_list, pos, sumup=True)`` (demag.py:456-463, SURVEY.md 8f rank 3;
+``mmr_field_currents``).  Cuboid magnets, Polyline and Circle currents; no CPU fallback.
 """
 
 from __future__ import annotations
@@ -9,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _native
-from ._compat import BaseCurrent, BaseMagnet, Collection, Cuboid, Sensor
+from ._compat import BaseCurrent, BaseMagnet, Circle, Collection, Cuboid, Polyline, Sensor
 
 
 def _flatten_sources(sources):
@@ -58,28 +59,83 @@ def cell_arrays(cells):
     return pos, quat, dim, pol
 
 
+def current_arrays(currents):
+    """Current sources as the arrays ``mmr_field_currents`` takes: Polyline vertices moved to the
+    global frame and split into segments (nseg,7) = (p1, p2, I); Circles (nloop,9) = (centre, quat
+    scalar-last, diameter, I).  Sources without a current / vertices / diameter contribute nothing
+    (magpylib evaluates them as zero)."""
+    segs, loops = [], []
+    for c in currents:
+        if np.ndim(c.position) != 1:
+            msg = "objects with paths are not supported by the B200 field kernel"
+            raise ValueError(msg)
+        cur = 0.0 if c.current is None else float(c.current)
+        if isinstance(c, Polyline):
+            if c.vertices is None:
+                continue
+            v = c.orientation.apply(np.asarray(c.vertices, dtype=float)) + np.asarray(c.position, dtype=float)
+            segs.extend([*a, *b, cur] for a, b in zip(v[:-1], v[1:], strict=True))
+        elif isinstance(c, Circle):
+            if c.diameter is None:
+                continue
+            loops.append([*np.asarray(c.position, dtype=float), *c.orientation.as_quat(), float(c.diameter), cur])
+        else:
+            msg = f"the B200 current-field kernel evaluates Polyline and Circle sources; found {type(c).__name__}"
+            raise NotImplementedError(msg)
+    return np.array(segs, dtype=float).reshape(-1, 7), np.array(loops, dtype=float).reshape(-1, 9)
+
+
+def current_field(field, currents, points, device=None, ctx=None):
+    """Summed B (tesla) or H (A/m) of the current sources at ``points`` (m,3) -> (m,3) numpy."""
+    seg, loop = current_arrays(currents)
+    pts = np.ascontiguousarray(points, dtype=float).reshape(-1, 3)
+    if len(pts) == 0 or (len(seg) == 0 and len(loop) == 0):
+        return np.zeros((len(pts), 3))
+    ctx = _native.default_context(device) if ctx is None else ctx
+    out = np.zeros((len(pts), 3))
+    d_pts = ctx.to_device(pts)
+    # the kernel stages its sources in shared memory: feed long polylines in chunks
+    chunk = 3000
+    for s0 in range(0, max(len(seg), 1), chunk):
+        sl = seg[s0:s0 + chunk]
+        lp = loop if s0 == 0 else loop[:0]
+        if len(sl) == 0 and len(lp) == 0:
+            continue
+        d_out = ctx.empty(len(pts), 3)
+        ctx.field_currents(d_pts, ctx.to_device(sl) if len(sl) else None, ctx.to_device(lp) if len(lp) else None,
+                           d_out, _native.FIELD_B if field == "B" else _native.FIELD_H)
+        out += d_out.cpu().numpy()
+    return out
+
+
 def getBH(field, sources, observers, sumup=True, squeeze=True, device=None):
-    """Field of cuboid sources at the observers, summed over sources (what
-    ``Collection.getB`` returns).  ``field`` is "B" (tesla) or "H" (A/m)."""
+    """Field of the sources at the observers, summed over sources (what ``Collection.getB``
+    returns).  ``field`` is "B" (tesla) or "H" (A/m)."""
     if field not in ("B", "H"):
         msg = "field must be 'B' or 'H'"
         raise ValueError(msg)
     srcs = _flatten_sources(sources)
-    bad = [s for s in srcs if not isinstance(s, Cuboid)]
+    cuboids = [s for s in srcs if isinstance(s, Cuboid)]
+    currents = [s for s in srcs if isinstance(s, BaseCurrent)]
+    bad = [s for s in srcs if not isinstance(s, Cuboid | BaseCurrent)]
     if bad:
         kinds = sorted({type(s).__name__ for s in bad})
-        if any(isinstance(s, BaseCurrent) for s in bad) or any(isinstance(s, BaseMagnet) for s in bad):
+        if any(isinstance(s, BaseMagnet) for s in bad):
             msg = f"the B200 field kernel evaluates Cuboid cells only; found {kinds}"
             raise NotImplementedError(msg)
         msg = f"unsupported source objects {kinds}"
         raise TypeError(msg)
     pts, shape = _observer_array(observers)
     ctx = _native.default_context(device)
-    pos, quat, dim, pol = cell_arrays(srcs)
-    d_out = ctx.empty(len(pts), 3)
-    ctx.field(
-        ctx.to_device(pos), ctx.to_device(quat), ctx.to_device(dim), ctx.to_device(pol),
-        ctx.to_device(pts), d_out, _native.FIELD_B if field == "B" else _native.FIELD_H,
-    )
-    out = d_out.cpu().numpy().reshape(*shape, 3)
-    return out
+    out = np.zeros((len(pts), 3))
+    if cuboids:
+        pos, quat, dim, pol = cell_arrays(cuboids)
+        d_out = ctx.empty(len(pts), 3)
+        ctx.field(
+            ctx.to_device(pos), ctx.to_device(quat), ctx.to_device(dim), ctx.to_device(pol),
+            ctx.to_device(pts), d_out, _native.FIELD_B if field == "B" else _native.FIELD_H,
+        )
+        out += d_out.cpu().numpy()
+    if currents:
+        out += current_field(field, currents, pts, ctx=ctx)
+    return out.reshape(*shape, 3)

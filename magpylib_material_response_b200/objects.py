@@ -282,11 +282,44 @@ class BaseMagnet(BaseSource):
 
 
 class BaseCurrent(BaseSource):
-    """Current-source marker class (current sources are not evaluated by the B200 path)."""
+    """Base of the line-current sources (magpylib.current.*)."""
 
     def __init__(self, position=(0.0, 0.0, 0.0), orientation=None, current=None, style=None, **kwargs):
         super().__init__(position, orientation, style, **kwargs)
         self.current = current
+
+
+class Polyline(BaseCurrent):
+    """magpylib.current.Polyline stand-in: straight segments through ``vertices`` (local frame, m)."""
+
+    def __init__(self, position=(0.0, 0.0, 0.0), orientation=None, vertices=None, current=None, style=None,
+                 **kwargs):
+        super().__init__(position, orientation, current, style, **kwargs)
+        self.vertices = vertices
+
+    @property
+    def vertices(self):
+        return self._vertices
+
+    @vertices.setter
+    def vertices(self, value):
+        if value is None:
+            self._vertices = None
+            return
+        arr = np.array(value, dtype=float)
+        if arr.ndim != 2 or arr.shape[1] != 3 or arr.shape[0] < 2:
+            msg = f"vertices must have shape (n>=2, 3), got {arr.shape}"
+            raise ValueError(msg)
+        self._vertices = arr
+
+
+class Circle(BaseCurrent):
+    """magpylib.current.Circle stand-in: loop of ``diameter`` (m) in the local xy plane."""
+
+    def __init__(self, position=(0.0, 0.0, 0.0), orientation=None, diameter=None, current=None, style=None,
+                 **kwargs):
+        super().__init__(position, orientation, current, style, **kwargs)
+        self.diameter = None if diameter is None else float(diameter)
 
 
 class Cuboid(BaseMagnet):
