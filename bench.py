@@ -94,6 +94,33 @@ def make_workload(name):
         return dict(pos=p, quat=q, dim=d, pol=np.zeros((m, 3)), chi=np.full((m, 3), 1000.0),
                     H_ext=np.tile((0, 0, 1.0), (m, 1)),
                     desc=f"soft-iron cube chi=1000, H_ext=(0,0,1), {a}x{a}x{a} = {m} cells")
+    if name.startswith("lattice_"):
+        # BASELINE configs[2]: k x k x k lattice of 1 mm cubes, pitch 1.5 mm, each meshed
+        # a x a x a identical cells, J = (0,0,1) T, anisotropic chi = (0.3, 0.2, 0.1); run with pairs_matching.
+        # lattice_27000 = 3^3 magnets x 10^3 cells; lattice_<k>x<a> builds reduced sizes for the parity tests.
+        spec = name.split("_")[1]
+        k, a = (int(v) for v in spec.split("x")) if "x" in spec else (3, round((int(spec) / 27) ** (1 / 3)))
+        parts = [mesh_arrays((1e-3,) * 3, (a, a, a), position=(1.5e-3 * i, 1.5e-3 * j, 1.5e-3 * l))
+                 for i in range(k) for j in range(k) for l in range(k)]
+        p_, q_, d_ = (np.vstack([pt[c] for pt in parts]) for c in range(3))
+        m = len(p_)
+        return dict(pos=p_, quat=q_, dim=d_, pol=np.tile((0, 0, 1.0), (m, 1)), chi=np.tile((0.3, 0.2, 0.1), (m, 1)),
+                    H_ext=np.zeros((m, 3)), pairs_matching=True,
+                    desc=f"{k}x{k}x{k} lattice of 1 mm cubes, pitch 1.5 mm, each {a}x{a}x{a} cells = {m} cells, "
+                         "chi=(0.3,0.2,0.1), pairs_matching")
+    if name.startswith("array_"):
+        # BASELINE configs[4]: k x k planar array of 1 mm cubes, pitch 2 mm, each a^3 cells,
+        # J = (0,0,1) T, chi = 0.5, max_dist truncation (pairs farther than max_dist cell edges are dropped) and
+        # split chunking.  array_51200 = 10x10 magnets x 8^3 cells; array_<k>x<a> for reduced sizes.
+        spec = name.split("_")[1]
+        k, a = (int(v) for v in spec.split("x")) if "x" in spec else (10, round((int(spec) / 100) ** (1 / 3)))
+        parts = [mesh_arrays((1e-3,) * 3, (a, a, a), position=(2e-3 * i, 2e-3 * j, 0.0)) for i in range(k) for j in range(k)]
+        p_, q_, d_ = (np.vstack([pt[c] for pt in parts]) for c in range(3))
+        m = len(p_)
+        return dict(pos=p_, quat=q_, dim=d_, pol=np.tile((0, 0, 1.0), (m, 1)), chi=np.full((m, 3), 0.5),
+                    H_ext=np.zeros((m, 3)), max_dist=12.0, split=8,
+                    desc=f"{k}x{k} planar array of 1 mm cubes, pitch 2 mm, each {a}x{a}x{a} cells = {m} cells, "
+                         "chi=0.5, max_dist=12, split=8")
     msg = f"unknown workload {name}"
     raise ValueError(msg)
 

@@ -4,12 +4,17 @@
 // (81.6 GB at n = 27000).  Here the unique pairs are found with a lock-free open-addressing table
 // on the device, keyed like the reference:  rint((p_j - p_i + 1e-9) * 1e8) per axis (= its
 // "(x + 1e-9).round(8)") plus the source cell's class id (rounded orientation + dimension, computed
-// on the host over n rows).  A slot stores one member pair (enough to
-// recompute the key for comparison) and, via atomicMin, the smallest flat index i*n+j of the class --
-// the same representative np.unique(return_index=True) picks.  Then
-//   1. insert all n^2 pairs            (L2-resident table, one atomic per new class)
+// on the host over n rows).  A slot IS the key: 128 bits (three 32-bit
+// displacements in units of 1e-8 m = +-21 m, 31-bit class id, valid bit) claimed with one 128-bit
+// compare-and-swap (ATOMG.CAS.128), so a probe is a single 16-byte load and compare.  A parallel
+// array keeps, via atomicMin, the smallest flat index i*n+j of the class -- the representative
+// np.unique(return_index=True) picks.  Then
+//   1. insert all n^2 pairs, remembering each pair's slot (4 B per pair, coalesced)
 //   2. evaluate one 3x3 block per class (the only transcendental work)
-//   3. scatter blocks to all pairs      (72 B written per pair: HBM-write bound)
+//   3. scatter blocks to all pairs      (72 B written + 4 B read per pair: HBM-write bound)
+// (The first version stored a member pair per slot and re-derived its key at every probe -- a 64-bit
+// division and six scattered loads -- and looked every pair up twice: 85 ms at n = 27000, slower
+// than evaluating all pairs densely.)
 #include "cuboid.cuh"
 
 namespace {
@@ -27,67 +32,70 @@ struct MatchParams {
   const double* chi;
   double* out;
   int64_t ld;
-  u64* tab;      // member pair index + 1, 0 = empty
-  u64* minrep;   // smallest pair index of the class
-  double* blocks;  // 9 doubles per slot
-  u64 mask;      // capacity - 1 (capacity is a power of two)
-  int* status;   // [0] = number of classes, [1] = overflow flag
+  u64* tab;        // 2 x u64 per slot: packed key, (0, 0) = empty
+  u64* minrep;     // smallest pair index of the class
+  double* blocks;  // 8 doubles (64 B) per slot: xx, xy, xz, yy, yz, zz of the symmetric block + padding
+  unsigned* slot_of_pair;  // [j*n + i] slot of pair (source i, observer j), or NULL (look up again)
+  u64 mask;        // capacity - 1 (capacity is a power of two)
+  int* status;     // [0] = number of classes, [1] = overflow flag, [2] = key out of range
   int rotated;
 };
 
 struct PairKey {
-  long long kx, ky, kz;
-  int cls;
+  u64 lo, hi;  // lo = kx | ky << 32, hi = kz | cls << 32 | valid bit 63
+  bool ok;     // every component fits its field
 };
 
 __device__ __forceinline__ PairKey make_key(const MatchParams& p, int64_t i, int64_t j) {
-  PairKey k;
   // (p_j - p_i + 1e-9).round(8): numpy rounds via rint(x * 1e8) / 1e8
-  k.kx = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 0], p.pos[3 * i + 0]), 1e-9), 1e8));
-  k.ky = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 1], p.pos[3 * i + 1]), 1e-9), 1e8));
-  k.kz = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 2], p.pos[3 * i + 2]), 1e-9), 1e8));
-  k.cls = p.cls[i];
+  const long long kx = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 0], p.pos[3 * i + 0]), 1e-9), 1e8));
+  const long long ky = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 1], p.pos[3 * i + 1]), 1e-9), 1e8));
+  const long long kz = __double2ll_rn(__dmul_rn(__dadd_rn(__dsub_rn(p.pos[3 * j + 2], p.pos[3 * i + 2]), 1e-9), 1e8));
+  const int cls = p.cls[i];
+  PairKey k;
+  k.ok = (kx == (long long)(int)kx) && (ky == (long long)(int)ky) && (kz == (long long)(int)kz) && cls >= 0;
+  k.lo = (u64)(unsigned)(int)kx | ((u64)(unsigned)(int)ky << 32);
+  k.hi = (u64)(unsigned)(int)kz | ((u64)(unsigned)cls << 32) | (1ull << 63);
   return k;
 }
 
-__device__ __forceinline__ bool same_key(const PairKey& a, const PairKey& b) {
-  return a.kx == b.kx && a.ky == b.ky && a.kz == b.kz && a.cls == b.cls;
-}
-
 __device__ __forceinline__ u64 hash_key(const PairKey& k) {
-  u64 h = (u64)k.kx * 0x9E3779B97F4A7C15ull;
-  h ^= (u64)k.ky + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-  h *= 0xC2B2AE3D27D4EB4Full;
-  h ^= (u64)k.kz + 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
-  h *= 0x9E3779B97F4A7C15ull;
-  h ^= (u64)(unsigned)k.cls + (h << 6) + (h >> 2);
+  u64 h = k.lo * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 32;
+  h += k.hi * 0xC2B2AE3D27D4EB4Full;
   h ^= h >> 29;
   h *= 0xBF58476D1CE4E5B9ull;
   h ^= h >> 32;
   return h;
 }
 
-// slot of the class of pair (i,j); inserts if INSERT.  Returns ~0 on overflow.
+__device__ __forceinline__ void cas128(u64* addr, u64 new_lo, u64 new_hi, u64& old_lo, u64& old_hi) {
+  // compare with (0, 0) = empty slot
+  asm volatile(
+      "{\n\t.reg .b128 e, n, o;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], e, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old_lo), "=l"(old_hi)
+      : "l"(0ull), "l"(0ull), "l"(new_lo), "l"(new_hi), "l"(addr)
+      : "memory");
+}
+
+// slot of the class of pair (i,j); inserts if INSERT.  Returns ~0 on overflow / missing.
 template <bool INSERT>
-__device__ __forceinline__ u64 find_slot(const MatchParams& p, int64_t i, int64_t j) {
-  const PairKey key = make_key(p, i, j);
-  const u64 me = (u64)(i * p.n + j);
+__device__ __forceinline__ u64 find_slot(const MatchParams& p, const PairKey& key, u64 me) {
   u64 h = hash_key(key) & p.mask;
   for (u64 probes = 0; probes <= p.mask; ++probes) {
-    u64 cur = p.tab[h];
-    if (cur == 0) {
+    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(p.tab + 2 * h));  // L2: where the CAS lands
+    u64 lo = cur.x, hi = cur.y;
+    if (hi == 0) {  // empty (a valid key has bit 63 of hi set)
       if (!INSERT) return ~0ull;
-      const u64 old = atomicCAS(&p.tab[h], 0ull, me + 1);
-      if (old == 0) {
+      cas128(p.tab + 2 * h, key.lo, key.hi, lo, hi);
+      if (hi == 0) {
         atomicAdd(&p.status[0], 1);
         atomicMin(&p.minrep[h], me);
         return h;
       }
-      cur = old;
     }
-    const u64 member = cur - 1;
-    const PairKey other = make_key(p, (int64_t)(member / (u64)p.n), (int64_t)(member % (u64)p.n));
-    if (same_key(key, other)) {
+    if (lo == key.lo && hi == key.hi) {
       if (INSERT && me < p.minrep[h]) atomicMin(&p.minrep[h], me);
       return h;
     }
@@ -96,12 +104,20 @@ __device__ __forceinline__ u64 find_slot(const MatchParams& p, int64_t i, int64_
   return ~0ull;
 }
 
+// thread = source i (fast index, so the slot record [j*n + i] is written coalesced), loop over observers
 __global__ void __launch_bounds__(256) match_insert_kernel(const MatchParams p) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // observer (fast index)
-  if (j >= p.n) return;
-  for (int64_t i = blockIdx.y; i < p.n; i += gridDim.y) {  // source
-    if (p.status[1]) return;
-    if (find_slot<true>(p, i, j) == ~0ull) atomicExch(&p.status[1], 1);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  for (int64_t j = blockIdx.y; j < p.n; j += gridDim.y) {
+    if (p.status[1] | p.status[2]) return;
+    const PairKey key = make_key(p, i, j);
+    if (!key.ok) {
+      atomicExch(&p.status[2], 1);
+      return;
+    }
+    const u64 h = find_slot<true>(p, key, (u64)(i * p.n + j));
+    if (h == ~0ull) atomicExch(&p.status[1], 1);
+    else if (p.slot_of_pair) p.slot_of_pair[j * p.n + i] = (unsigned)h;
     // load factor guard: stop early once the table is more than half full
     if (threadIdx.x == 0 && (u64)p.status[0] * 2 > p.mask + 1) atomicExch(&p.status[1], 1);
   }
@@ -110,7 +126,7 @@ __global__ void __launch_bounds__(256) match_insert_kernel(const MatchParams p) 
 __global__ void __launch_bounds__(128) match_eval_kernel(const MatchParams p) {
   const u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (h > p.mask) return;
-  if (p.tab[h] == 0) return;
+  if (p.tab[2 * h + 1] == 0) return;
   const u64 rep = p.minrep[h];
   const int64_t i = (int64_t)(rep / (u64)p.n), j = (int64_t)(rep % (u64)p.n);
   const double dx = p.pos[3 * j + 0] - p.pos[3 * i + 0];
@@ -133,8 +149,12 @@ __global__ void __launch_bounds__(128) match_eval_kernel(const MatchParams p) {
     blk[3] = N.xy; blk[4] = N.yy; blk[5] = N.yz;
     blk[6] = N.xz; blk[7] = N.yz; blk[8] = N.zz;
   }
-#pragma unroll
-  for (int q = 0; q < 9; ++q) p.blocks[h * 9 + q] = blk[q];
+  // R N R^T is symmetric like N: 6 values, one 64-byte line per class (two sectors per gather
+  // instead of nine scattered 8-byte loads)
+  double2* dst = reinterpret_cast<double2*>(p.blocks + h * 8);
+  dst[0] = make_double2(blk[0], blk[1]);
+  dst[1] = make_double2(blk[2], blk[4]);
+  dst[2] = make_double2(blk[5], blk[8]);
 }
 
 template <bool FUSE_Q>
@@ -156,10 +176,21 @@ __global__ void __launch_bounds__(SRC_TILE) match_scatter_kernel(const MatchPara
   const int64_t ncols_warp = min((int64_t)96, 3 * (p.n - i_warp0));
   for (int tt = 0; tt < ntgt; ++tt) {
     const int64_t j = t0 + tt;
-    const u64 h = find_slot<false>(p, ic, j);
+    const u64 h = p.slot_of_pair ? (u64)p.slot_of_pair[j * p.n + ic]
+                                 : find_slot<false>(p, make_key(p, ic, j), 0ull);
     double blk[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) blk[q] = (h != ~0ull) ? p.blocks[h * 9 + q] : 0.0;
+    {
+      double2 a = make_double2(0.0, 0.0), b = a, c = a;
+      if (h != ~0ull) {
+        const double2* src = reinterpret_cast<const double2*>(p.blocks + h * 8);
+        a = src[0];
+        b = src[1];
+        c = src[2];
+      }
+      blk[0] = a.x; blk[1] = a.y; blk[2] = b.x;
+      blk[3] = a.y; blk[4] = b.y; blk[5] = c.x;
+      blk[6] = b.x; blk[7] = c.x; blk[8] = c.y;
+    }
     if (FUSE_Q) {
       const bool diag = (j == i);
 #pragma unroll
@@ -213,14 +244,16 @@ extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos
   rc = mmr_detect_rotated(ctx, n, d_quat, &rotated);
   if (rc) return rc;
 
-  // capacity: power of two, grown on overflow up to table_cap_slots
-  u64 cap = 1ull << 16;
-  while (cap < 4096ull * 16 && cap < (u64)table_cap_slots) cap <<= 1;
+  // capacity: power of two, grown on overflow up to table_cap_slots (88 B per slot)
   const u64 npairs = (u64)n * (u64)n;
+  u64 cap = 1ull << 16;
+  while (cap < (1ull << 21) && cap < 4 * npairs) cap <<= 1;
+  // one slot id per pair, so the scatter pass needs no second lookup (skipped beyond 12 GB)
+  const size_t slot_bytes = (sizeof(unsigned) * npairs <= (size_t)12e9) ? ((sizeof(unsigned) * npairs + 255) / 256) * 256 : 0;
   for (;;) {
     while (cap > (u64)table_cap_slots) cap >>= 1;
-    const size_t bytes = 256 + cap * (sizeof(u64) * 2 + sizeof(double) * 9);
-    rc = mmr_ws2_reserve(ctx, bytes);
+    const size_t tab_bytes = 256 + cap * (sizeof(u64) * 3 + sizeof(double) * 8);
+    rc = mmr_ws2_reserve(ctx, tab_bytes + slot_bytes);
     if (rc) return rc;
     char* base = (char*)ctx->ws2;
     MatchParams p;
@@ -228,20 +261,25 @@ extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos
     p.out = d_out; p.ld = ld;
     p.status = (int*)base;
     p.tab = (u64*)(base + 256);
-    p.minrep = p.tab + cap;
+    p.minrep = p.tab + 2 * cap;
     p.blocks = (double*)(p.minrep + cap);
+    p.slot_of_pair = slot_bytes ? (unsigned*)(base + tab_bytes) : nullptr;
     p.mask = cap - 1;
     p.rotated = rotated;
     MMR_CUDA(cudaMemsetAsync(p.status, 0, 256, ctx->stream));
-    MMR_CUDA(cudaMemsetAsync(p.tab, 0, sizeof(u64) * cap, ctx->stream));
+    MMR_CUDA(cudaMemsetAsync(p.tab, 0, sizeof(u64) * 2 * cap, ctx->stream));
     MMR_CUDA(cudaMemsetAsync(p.minrep, 0xff, sizeof(u64) * cap, ctx->stream));
-    dim3 gi((unsigned)ceil_div64(n, 256), (unsigned)(n < 32768 ? n : 32768));
+    dim3 gi((unsigned)ceil_div64(n, 256), (unsigned)(n < 2048 ? n : 2048));
     match_insert_kernel<<<gi, 256, 0, ctx->stream>>>(p);
     MMR_CHECK_LAUNCH(ctx);
-    MMR_CUDA(cudaMemcpyAsync(ctx->hpin, p.status, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMR_CUDA(cudaMemcpyAsync(ctx->hpin, p.status, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MMR_CUDA(cudaStreamSynchronize(ctx->stream));
     const int nclasses = ((int*)ctx->hpin)[0];
     const int overflow = ((int*)ctx->hpin)[1];
+    if (((int*)ctx->hpin)[2]) {
+      mmr_set_error("pairs_matching: a pair displacement exceeds the +-21 m key range (1e-8 m units in 32 bits)");
+      return -3;
+    }
     if (overflow) {
       if (cap * 2 > (u64)table_cap_slots || cap >= 2 * npairs) {
         mmr_set_error("pairs_matching: more than %llu unique pairs (table cap %lld slots)",

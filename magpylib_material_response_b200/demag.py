@@ -187,9 +187,19 @@ def filter_distance(src_list, max_dist, min_log_time=None, return_params=False, 
 
 def _source_classes(quat, dim):
     """Integer class id per cell: cells with the same (rounded) orientation and dimension."""
-    key = (np.concatenate([quat, dim], axis=1) + 1e-9).round(8)
-    _, cls = np.unique(key, axis=0, return_inverse=True)
-    return np.asarray(cls).reshape(-1).astype(np.int32)
+    key = (np.concatenate([quat, dim], axis=1) + 1e-9).round(8) + 0.0  # "+ 0.0": -0.0 -> +0.0
+    # np.unique(axis=0) sorts 7-column rows (47 ms at n = 27000): hash the rows to one uint64, take the
+    # unique hashes, and verify that every row equals its class representative (else fall back)
+    mult = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0xBF58476D1CE4E5B9,
+                     0x94D049BB133111EB, 0xD6E8FEB86659FD93, 0xFF51AFD7ED558CCD], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h = (np.ascontiguousarray(key).view(np.uint64) * mult).sum(axis=1, dtype=np.uint64)
+    _, first, cls = np.unique(h, return_index=True, return_inverse=True)
+    cls = np.asarray(cls).reshape(-1)
+    if not np.array_equal(key[first][cls], key):  # a 64-bit hash collision
+        _, cls = np.unique(key, axis=0, return_inverse=True)
+        cls = np.asarray(cls).reshape(-1)
+    return cls.astype(np.int32)
 
 
 def match_pairs(src_list, min_log_time=None):

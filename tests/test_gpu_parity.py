@@ -469,6 +469,50 @@ def test_apply_demag_random_anisotropic_stress_vs_oracle():
 # ---------------------------------------------------------------------------------------
 # full BASELINE size (n = 8000, N = 24000): size-independent properties
 # ---------------------------------------------------------------------------------------
+def test_config3_lattice_anisotropic_pairs_matching_reduced_vs_oracle():
+    """BASELINE configs[2] geometry at reduced size (2x2x2 magnets x 5^3 cells; the CPU match_pairs needs
+    n^2 x 14 doubles): anisotropic chi, pairs_matching=True, LU and GMRES, against the oracle's own
+    match_pairs restatement (demag.py:280-321)."""
+    from bench import make_workload
+
+    w = make_workload("lattice_2x5")
+    n = len(w["pos"])
+    assert n == 1000 and w["pairs_matching"]
+    ref = oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], pairs_matching=True)
+    ref_dense = oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], split=4)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(ref - ref_dense) / scale) < 1e-6  # the reference's own 1e-8 m key rounding
+    for solver in ("lu", "gmres"):
+        got, info = mmr.demag.apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"],
+                                                 pairs_matching=True, solver=solver, tol=1e-13, return_info=True)
+        assert np.max(np.abs(got - ref_dense) / scale) <= J_RTOL, solver
+    # mirror symmetry of the lattice: J_z even, J_x odd under x -> -x
+    ctr = w["pos"].mean(axis=0)
+    key = np.round((w["pos"] - ctr) * 1e9).astype(np.int64)
+    mir = key * np.array([-1, 1, 1])
+    perm = np.empty(n, dtype=np.int64)
+    perm[np.lexsort(key.T[::-1])] = np.lexsort(mir.T[::-1])
+    assert np.abs(got[:, 2] - got[perm][:, 2]).max() <= 1e-12 and np.abs(got[:, 0] + got[perm][:, 0]).max() <= 1e-12
+
+
+def test_config5_magnet_array_max_dist_split_reduced_vs_oracle():
+    """BASELINE configs[4] geometry at reduced size (3x3 magnets x 4^3 cells): max_dist truncation with the
+    repaired semantics and split chunking, against the oracle."""
+    from bench import make_workload
+
+    w = make_workload("array_3x4")
+    n = len(w["pos"])
+    assert n == 576 and w["max_dist"] == 12.0 and w["split"] == 8
+    ref = oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], max_dist=12.0, split=8)
+    full = oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"])
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(ref - full) / scale) > 1e-6  # the truncation really removes pairs
+    for solver, split in (("lu", 8), ("lu", 1), ("gmres", 8)):
+        got = mmr.demag.apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"],
+                                           max_dist=12.0, split=split, solver=solver, tol=1e-13)
+        assert np.max(np.abs(got - ref) / scale) <= J_RTOL, (solver, split)
+
+
 def test_config2prime_8000_cells_properties(ctx):
     """North-star target config: soft-iron cube 20x20x20, chi=1000, H_ext=(0,0,1)."""
     cube = Cuboid(dimension=(1e-3,) * 3, polarization=(0, 0, 0))
