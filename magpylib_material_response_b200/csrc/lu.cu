@@ -1033,13 +1033,12 @@ size_t mmr_lu_panel_scratch_bytes() { return 2 * 256 * sizeof(Cand) + (2 * 256 *
 // =======================================================================================
 namespace {
 
-// 1/a without the division slow path: MUFU.RCP64H seed (20 bits) + Newton steps (20 -> 40 -> 80 bits, a
-// third one absorbs the seed's worst case), straight-line so that it overlaps the independent DFMAs
-// around it (LAPACK's dgetf2 also scales by a reciprocal).
+// 1/a without the division slow path: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (-> 40 -> 80
+// bits), straight-line so that it overlaps the independent DFMAs around it; it sits on the critical
+// path of every elimination step.  (LAPACK's dgetf2 also scales by a reciprocal.)
 __device__ __forceinline__ double fast_rcp(double a) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  x = fma(x, fma(-a, x, 1.0), x);
   x = fma(x, fma(-a, x, 1.0), x);
   x = fma(x, fma(-a, x, 1.0), x);
   return x;
@@ -1161,17 +1160,18 @@ __global__ void __launch_bounds__(256)
   const int nc = min(TINV_COLS, nb - cb);
   // lower-triangular T in Ls[c*(nb+1) + r] (r >= c).  L: T(r, c) = S[c*lds + r] (unit diagonal);
   // U: T = U^T, T(r, c) = U(c, r) = S[r*lds + c].  `f` is the fast (contiguous) index of S.
-  for (int base = 0; base < nb * nb; base += 8 * 256) {
-    double tmp[8];
+  constexpr int INFLIGHT = 16;  // independent loads per thread and round trip
+  for (int base = 0; base < nb * nb; base += INFLIGHT * 256) {
+    double tmp[INFLIGHT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < INFLIGHT; ++k) {
       const int e = base + tid + k * 256;
       const int f = e % nb, g = e / nb;  // S[g*lds + f]
       const bool need = (e < nb * nb) && (upper ? (g >= f) : (f > g));
       tmp[k] = need ? __ldg(S + (int64_t)g * lds + f) : 1.0;  // L: the unit diagonal
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < INFLIGHT; ++k) {
       const int e = base + tid + k * 256;
       const int f = e % nb, g = e / nb;
       if (e < nb * nb) {
@@ -1218,12 +1218,25 @@ __global__ void __launch_bounds__(256)
       double x[TB];
 #pragma unroll
       for (int i = 0; i < TB; ++i) x[i] = (i < tb) ? Bs[c * (nb + 1) + t0 + i] : 0.0;
-      for (int r = t0 + tb + rg; r < nb; r += RG) {
-        double acc = 0.0;
+      // four rows per pass: four independent accumulation chains instead of one
+      for (int r0 = t0 + tb + rg; r0 < nb; r0 += 4 * RG) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int qq = 0; qq < TB; ++qq)
-          if (qq < tb) acc += Ls[(t0 + qq) * (nb + 1) + r] * x[qq];
-        Bs[c * (nb + 1) + r] -= acc;
+        for (int qq = 0; qq < TB; ++qq) {
+          if (qq < tb) {
+            const double* lrow = Ls + (t0 + qq) * (nb + 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = r0 + k * RG;
+              if (r < nb) acc[k] += lrow[r] * x[qq];
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = r0 + k * RG;
+          if (r < nb) Bs[c * (nb + 1) + r] -= acc[k];
+        }
       }
     }
     __syncthreads();
