@@ -211,7 +211,7 @@ template <bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_fast_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                          const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                         int64_t ldc, int stagger_ns, int sm_count) {
+                         int64_t ldc, int prefetch_dist) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
@@ -219,13 +219,6 @@ __global__ void __launch_bounds__(THREADS, 2)
   const int wm = warp & 3, wn = warp >> 2;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int KT = k / BK;
-  // De-phase the two CTAs that share an SM: in the first wave the second CTA of every SM starts
-  // half a tile later; every later CTA inherits the offset of the slot it replaces, so one CTA's
-  // load/store phases fall into the other's DMMA phase instead of coinciding with them.
-  if (stagger_ns > 0) {
-    const int lin = blockIdx.x + blockIdx.y * gridDim.x;
-    if (lin >= sm_count && lin < 2 * sm_count) __nanosleep(stagger_ns);
-  }
 
   double acc[4][4][2];
   if (SUBTRACT) {
@@ -286,6 +279,21 @@ __global__ void __launch_bounds__(THREADS, 2)
       copy_b(s, s);
     }
     cp_async_commit();
+  }
+  if (SUBTRACT && prefetch_dist > 0) {
+    // CTAs are dispatched in linear order, so the CTA that will take over this SM slot when this one
+    // retires is about `prefetch_dist` (= resident CTAs of the grid) tiles ahead: pull its C tile
+    // (64 columns x 8 lines of 128 B) into L2 now, so that its accumulator loads do not pay DRAM latency
+    const int64_t nxt = (int64_t)blockIdx.x + (int64_t)blockIdx.y * gridDim.x + prefetch_dist;
+    if (nxt < (int64_t)gridDim.x * gridDim.y) {
+      const int pm0 = (int)(nxt % gridDim.x) * BM, pn0 = (int)(nxt / gridDim.x) * BN;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int line = tid + q * THREADS;
+        const int col = pn0 + (line >> 3), row = pm0 + (line & 7) * 16;
+        if (col < n && row < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (int64_t)col * ldc + row));
+      }
+    }
   }
   if (SUBTRACT) {
 #pragma unroll

@@ -827,20 +827,18 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
-  static int stagger_pct = -1;
-  if (stagger_pct < 0) {
-    const char* e = getenv("MMR_DGEMM_STAGGER_PCT");
-    stagger_pct = e ? atoi(e) : 0;  // measured: no effect on B200, kept as an experiment knob
+  static int prefetch_on = -1;
+  if (prefetch_on < 0) {
+    const char* e = getenv("MMR_DGEMM_PREFETCH");
+    prefetch_on = (e && e[0] == '0') ? 0 : 1;
   }
   if (fast && aligned && k > 0 && k % BK == 0) {
-    // tile time when two CTAs share the tensor pipe: 2*BM*BN*k FMA at 64 FMA/clk/SM, ~1.9 GHz
-    int stagger_ns = 0;
-    if (ntiles > 2 * (int64_t)ctx->sm_count)
-      stagger_ns = (int)((2.0 * BM * BN * (double)k / 64.0 / 1.9) * stagger_pct / 100.0);
+    // L2 prefetch distance for the C tiles: the number of CTAs resident at once (2 per SM)
+    const int pf = (prefetch_on && ntiles > 2 * (int64_t)ctx->sm_count) ? 2 * ctx->sm_count : 0;
     if (subtract)
-      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, stagger_ns, ctx->sm_count);
+      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf);
     else
-      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, stagger_ns, ctx->sm_count);
+      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }
