@@ -363,163 +363,6 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// Persistent LU-form kernel:  C <- C - A*B.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...
-// (m fastest, so concurrently running CTAs share the same B panel in L2).  The cp.async pipeline
-// is flattened over (tile, k-tile): the first stages of the next tile are already in flight while
-// the current tile finishes, and the next tile's C lines are prefetched into L2, so the per-tile
-// prologue bubble (DRAM latency of C + first A/B stage) of the one-tile-per-CTA kernel disappears.
-// ---------------------------------------------------------------------------------------
-template <bool ALIGNED16>
-__global__ void __launch_bounds__(THREADS, 2)
-    dgemm_lu_persistent_kernel(int m, int n, int k, const double* __restrict__ A, int64_t lda,
-                               const double* __restrict__ B, int64_t ldb, double* __restrict__ C,
-                               int64_t ldc) {
-  extern __shared__ __align__(16) double smem[];
-  double* As = smem;
-  double* Bs = smem + STAGES * A_STAGE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2;
-  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
-  const int ntiles = tiles_m * tiles_n;
-  const int KT = (k + BK - 1) / BK;
-  const int first = blockIdx.x, step = gridDim.x;
-  if (first >= ntiles) return;
-  const int n_my = (ntiles - first + step - 1) / step;
-  const int total_g = n_my * KT;
-
-  auto load_tile = [&](int stage, int tile, int kt) {
-    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-    const int k0 = kt * BK;
-    double* as = As + stage * A_STAGE;
-    double* bs = Bs + stage * B_STAGE;
-    if (ALIGNED16) {
-#pragma unroll
-      for (int it = 0; it < (BK * BM / 2) / THREADS; ++it) {
-        const int idx = tid + it * THREADS;
-        const int kr = idx / (BM / 2);
-        const int mc = (idx % (BM / 2)) * 2;
-        const int gm = m0 + mc, gk = k0 + kr;
-        int bytes = 0;
-        if (gk < k && gm < m) bytes = (m - gm >= 2) ? 16 : 8;
-        cp_async16(as + kr * LDA_S + mc, bytes ? (A + (int64_t)gk * lda + gm) : A, bytes);
-      }
-#pragma unroll
-      for (int it = 0; it < (BN * BK / 2) / THREADS; ++it) {
-        const int idx = tid + it * THREADS;
-        const int nr = idx / (BK / 2);
-        const int kc = (idx % (BK / 2)) * 2;
-        const int gn = n0 + nr, gk = k0 + kc;
-        int bytes = 0;
-        if (gn < n && gk < k) bytes = (k - gk >= 2) ? 16 : 8;
-        cp_async16(bs + nr * LDB_S + kc, bytes ? (B + (int64_t)gn * ldb + gk) : B, bytes);
-      }
-    } else {
-#pragma unroll
-      for (int it = 0; it < (BK * BM) / THREADS; ++it) {
-        const int idx = tid + it * THREADS;
-        const int kr = idx / BM, mc = idx % BM;
-        const int gm = m0 + mc, gk = k0 + kr;
-        const bool ok = (gk < k && gm < m);
-        cp_async8(as + kr * LDA_S + mc, ok ? (A + (int64_t)gk * lda + gm) : A, ok ? 8 : 0);
-      }
-#pragma unroll
-      for (int it = 0; it < (BN * BK) / THREADS; ++it) {
-        const int idx = tid + it * THREADS;
-        const int nr = idx / BK, kc = idx % BK;
-        const int gn = n0 + nr, gk = k0 + kc;
-        const bool ok = (gn < n && gk < k);
-        cp_async8(bs + nr * LDB_S + kc, ok ? (B + (int64_t)gn * ldb + gk) : B, ok ? 8 : 0);
-      }
-    }
-  };
-
-  // producer cursor (g_ld) runs STAGES-1 k-tiles ahead of the consumer
-  int ld_it = 0, ld_kt = 0, ld_stage = 0;
-  auto issue_next = [&]() {
-    if (ld_it < n_my) load_tile(ld_stage, first + ld_it * step, ld_kt);
-    cp_async_commit();
-    ld_stage = (ld_stage + 1 == STAGES) ? 0 : ld_stage + 1;
-    if (++ld_kt == KT) {
-      ld_kt = 0;
-      ++ld_it;
-    }
-  };
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue_next();
-
-  const int a_row = wm * 32 + (lane >> 2);
-  const int b_row = wn * 32 + (lane >> 2);
-  const int kq = lane & 3;
-  int cs = 0;  // consumer stage
-  (void)total_g;
-
-  for (int it = 0; it < n_my; ++it) {
-    const int tile = first + it * step;
-    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-    // L2 prefetch of the NEXT tile's C (64 columns x 1 KB): 512 lines, 2 per thread
-    if (it + 1 < n_my) {
-      const int nt = tile + step;
-      const int pm0 = (nt % tiles_m) * BM, pn0 = (nt / tiles_m) * BN;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int line = tid + q * THREADS;       // 0..511
-        const int col = pn0 + (line >> 3);          // 8 lines of 128 B per column
-        const int row = pm0 + (line & 7) * 16;
-        if (col < n && row < m) {
-          const double* ptr = C + (int64_t)col * ldc + row;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-        }
-      }
-    }
-    double acc[4][4][2];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int gm = m0 + wm * 32 + 8 * f + (lane >> 2);
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
-          acc[f][g][e] = (gm < m && gn < n) ? flip_sign(__ldcs(C + (int64_t)gn * ldc + gm)) : 0.0;
-        }
-    }
-    for (int kt = 0; kt < KT; ++kt) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      issue_next();
-      const double* as = As + cs * A_STAGE;
-      const double* bs = Bs + cs * B_STAGE;
-#pragma unroll
-      for (int kk = 0; kk < BK; kk += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) af[f] = as[(kk + kq) * LDA_S + a_row + 8 * f];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) bf[g] = bs[(b_row + 8 * g) * LDB_S + kk + kq];
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-#pragma unroll
-          for (int g = 0; g < 4; ++g) dmma884(acc[f][g][0], acc[f][g][1], af[f], bf[g]);
-      }
-      cs = (cs + 1 == STAGES) ? 0 : cs + 1;
-    }
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      const int gm = m0 + wm * 32 + 8 * f + (lane >> 2);
-      if (gm >= m) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
-          if (gn < n) C[(int64_t)gn * ldc + gm] = flip_sign(acc[f][g][e]);
-        }
-    }
-  }
-  cp_async_wait<0>();
-}
-
 }  // namespace mmr_gemm
 
 // host-side launcher (defined in lu.cu)

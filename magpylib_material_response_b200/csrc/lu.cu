@@ -813,13 +813,6 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
   }
   dim3 grid((unsigned)ceil_div64(m, BM), (unsigned)ceil_div64(n, BN));
   const int64_t ntiles = (int64_t)grid.x * grid.y;
-  static int persistent = -1;
-  if (persistent < 0) {
-    const char* e = getenv("MMR_DGEMM_PERSISTENT");
-    persistent = (e && e[0] == '1') ? 1 : 0;  // experiment, off by default (slower than the fast kernel)
-    MMR_CUDA(cudaFuncSetAttribute(dgemm_lu_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MMR_CUDA(cudaFuncSetAttribute(dgemm_lu_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  }
   static int fast = -1;
   if (fast < 0) {
     const char* e = getenv("MMR_DGEMM_FAST");
@@ -839,15 +832,6 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
       dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf);
     else
       dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf);
-    MMR_CHECK_LAUNCH(ctx);
-    return 0;
-  }
-  if (subtract && persistent && ntiles > 2 * (int64_t)ctx->sm_count) {
-    const unsigned pg = (unsigned)(2 * ctx->sm_count);
-    if (aligned)
-      dgemm_lu_persistent_kernel<true><<<pg, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, A, lda, B, ldb, C, ldc);
-    else
-      dgemm_lu_persistent_kernel<false><<<pg, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, A, lda, B, ldb, C, ldc);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }
@@ -1299,8 +1283,7 @@ int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, in
   double* Uinv = (double*)d_spec;
   int* d_flag = (int*)((char*)d_spec + sizeof(double) * NB * NB);
   const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, strm);
-  if (seg == 64) lu_diag_nopiv_kernel<64><<<1, 256, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
-  else if (seg == 16) lu_diag_nopiv_kernel<16><<<1, 1024, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
+  if (seg == 16) lu_diag_nopiv_kernel<16><<<1, 1024, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
   else lu_diag_nopiv_kernel<32><<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
   MMR_CHECK_LAUNCH(ctx);
   const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
