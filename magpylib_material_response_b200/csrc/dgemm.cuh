@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(THREADS, 2)
 // tensor-pipe execution.
 // Tried and rejected (measured on B200, m = n = 12288, k = 256): a persistent variant with an L2 prefetch of
 // the next C tile (57% tensor-pipe activity), de-phasing the two CTAs of an SM with a start-up delay
-// (no effect), and 64 x 64 tiles with 4 CTAs per SM (32.2 TF against 33.1 TF for this kernel).
+// (no effect), 64 x 64 tiles with 4 CTAs per SM (32.2 TF against 33.1 TF for this kernel), and BK = 32 with two
+// stages, i.e. half the CTA barriers at the same prefetch depth (31.1 TF).
 // ---------------------------------------------------------------------------------------
 template <bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
