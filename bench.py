@@ -175,12 +175,12 @@ def cpu_sample_workload(name, n_sample):
     return make_workload(f"{kind}_{n_sample}")
 
 
-def time_oracle_step(w, split):
+def time_oracle_step(w, split, stages=None):
     """One full reference step on the CPU: 3 getH passes, dense S@T, np.linalg.solve."""
     from oracle import demag_ref as oref
 
     t0 = time.perf_counter()
-    oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], H_ext=w["H_ext"], split=split)
+    oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], H_ext=w["H_ext"], split=split, timings=stages)
     return time.perf_counter() - t0
 
 
@@ -189,13 +189,19 @@ def cpu_baseline(name, budget_s=20.0):
     n_sample = 2000 if "two_magnets" in name else 1728
     w = cpu_sample_workload(name, n_sample)
     n = len(w["pos"])
-    t = time_oracle_step(w, split=4)
+    stages = {}
+    t = time_oracle_step(w, split=4, stages=stages)
     reps = 1
     while t * (reps + 1) < budget_s / 2 and reps < 3:
-        t = min(t, time_oracle_step(w, split=4))
+        st = {}
+        t2 = time_oracle_step(w, split=4, stages=st)
+        if t2 < t:
+            t, stages = t2, st
         reps += 1
     return {
         "value": 9.0 * n * n / t, "unit": "T-entries/s", "cores": os.cpu_count(), "kind": "port",
+        "stages_s": {k: round(v, 4) for k, v in stages.items()},
+        "assembly_entries_per_s": 9.0 * n * n / stages["assembly_s"],
         "sample": f"{w['desc']} (reduced from the full workload), full reference step "
                   f"(3 getH passes + dense S@T + LAPACK dgesv) in {t:.2f} s; numpy ufuncs run on 1 thread, BLAS/LAPACK on all cores",
         "seconds": t, "n_cells": n,

@@ -220,8 +220,10 @@ def apply_demag_ref(
     max_dist=0,
     split=1,
     return_parts=False,
+    timings=None,
 ):
-    """Solved LOCAL-frame polarizations (n,3).
+    """Solved LOCAL-frame polarizations (n,3).  ``timings``: optional dict that receives the wall seconds of the
+    three stages SURVEY 8d names (assembly, building Q with the dense S@T, LAPACK solve).
 
     Restates demag.py:420-476: J0 = R_i J_i stacked order="F" (:420-428), S = diag(chi)
     dense (:432), T (:444-452), Q = I - S@T via dense matmul (:466), np.linalg.solve
@@ -240,13 +242,21 @@ def apply_demag_ref(
     H_ext = np.broadcast_to(np.asarray(H_ext, dtype=float), (n, 3))
     H_ext_v = np.reshape(H_ext, (3 * n, 1), order="F")
 
+    import time as _time
+
+    t0 = _time.perf_counter()
     T4 = demag_tensor_ref(
         pos, quat, dim, pairs_matching=pairs_matching, split=split, max_dist=max_dist
     )
     T = tensor_to_matrix(T4)
+    t1 = _time.perf_counter()
     Q = np.eye(3 * n) - np.matmul(S, T)
     rhs = pol_magnets + np.matmul(S, H_ext_v)
+    t2 = _time.perf_counter()
     pol_new = np.linalg.solve(Q, rhs)
+    t3 = _time.perf_counter()
+    if timings is not None:
+        timings.update(assembly_s=t1 - t0, build_Q_s=t2 - t1, solve_s=t3 - t2)
     pol_new = np.reshape(pol_new, (n, 3), order="F")
     pol_loc = np.einsum("pji,pj->pi", Rm, pol_new)
     if return_parts:
