@@ -65,7 +65,7 @@ def _worker(rank, world, port, n_cells, tgt_block, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize(("n_cells", "tgt_block"), [(100, 8), (37, 40), (250, 40), (64, 32)])
+@pytest.mark.parametrize(("n_cells", "tgt_block"), [(100, 8), (37, 40), (250, 40), (64, 32), (500, 80), (173, 85)])
 def test_two_rank_gloo_ownership_bootstrap_and_matvec(n_cells, tgt_block):
     world = 2
     port = _free_port()
