@@ -114,21 +114,19 @@ def mesh_Cuboid(cuboid, target_elems, verbose=False, **kwargs):
 
 
 def get_volume(obj, return_containing_cube_edge=False):
-    """Object volume and the edge of the smallest origin-centred unrotated cube containing it
-    (meshing_utils.py:113-137; only the Cuboid branch exists on the B200 path)."""
-    if obj.__class__.__name__ != "Cuboid":
+    """Volume of a Cuboid and, on request, the edge of the smallest origin-centred axis-aligned cube
+    that contains it (meshing_utils.py:113-137; the B200 path has the Cuboid branch only)."""
+    if type(obj).__name__ != "Cuboid":
         msg = "Unsupported object type for volume calculation"
         raise TypeError(msg)
-    dim = obj.dimension
-    vol = dim[0] * dim[1] * dim[2]
-    if return_containing_cube_edge:
-        return vol, max(dim)
-    return vol
+    edges = np.asarray(obj.dimension, dtype=float)
+    volume = float(np.prod(edges))
+    return (volume, float(edges.max())) if return_containing_cube_edge else volume
 
 
 def slice_Cuboid(cuboid, shift=0.5, axis="z", **kwargs):
-    """Slice a Cuboid in two along ``axis`` at the relative position ``shift`` in (0, 1)
-    (meshing.py:247-304); returns a Collection of the two parts."""
+    """Cut a Cuboid in two with a plane normal to ``axis`` at the relative position ``shift`` in (0, 1),
+    measured from the low side (meshing.py:247-304).  Returns a Collection [low part, high part]."""
     if not isinstance(cuboid, Cuboid):
         msg = (
             "Object to be sliced must be a Cuboid, "
@@ -138,59 +136,49 @@ def slice_Cuboid(cuboid, shift=0.5, axis="z", **kwargs):
     if not 0 < shift < 1:
         msg = "Shift must be between 0 and 1 (exclusive)"
         raise ValueError(msg)
-    dim0 = cuboid.dimension
-    pol0 = cuboid.polarization
-    ind = "xyz".index(axis)
-    dim_k = dim0[ind]
-    dims_k = dim_k * (1 - shift), dim_k * shift
-    shift_k = (dim_k - dims_k[0]) / 2, -(dim_k - dims_k[1]) / 2
-    cells = []
-    for d, sh in zip(dims_k, shift_k, strict=True):
-        dimension = np.array(dim0, dtype=float)
-        dimension[ind] = d
-        position = np.zeros(3)
-        position[ind] = sh
-        cells.append(Cuboid(polarization=pol0, dimension=dimension, position=position))
-    return _collection_from_obj_and_cells(cuboid, cells[::-1], **kwargs)
+    k = "xyz".index(axis)
+    full = np.asarray(cuboid.dimension, dtype=float)
+    lo_edge = -full[k] / 2
+    parts = []
+    for frac0, frac1 in ((0.0, shift), (shift, 1.0)):  # low part first
+        size = full.copy()
+        size[k] = full[k] * (frac1 - frac0)
+        centre = np.zeros(3)
+        centre[k] = lo_edge + full[k] * (frac0 + frac1) / 2
+        parts.append(Cuboid(polarization=cuboid.polarization, dimension=size, position=centre))
+    return _collection_from_obj_and_cells(cuboid, parts, **kwargs)
+
+
+def _share_elements(cuboids, target_elems, min_elems, per_child_elems):
+    """Cells per cuboid: the same number for all, or ``target_elems`` split by volume fraction
+    (truncated), never below ``min_elems`` (meshing.py:418-424)."""
+    if per_child_elems:
+        return [max(min_elems, target_elems)] * len(cuboids)
+    vol = np.array([get_volume(c) for c in cuboids], dtype=float)
+    return [max(min_elems, int(v / vol.sum() * target_elems)) for v in vol]
 
 
 def mesh_all(obj, target_elems, min_elems=8, per_child_elems=False, inplace=False, **kwargs):
-    """Replace every Cuboid of ``obj`` (an object or a Collection tree) by its meshed Collection;
-    ``target_elems`` is shared among the children in proportion to their volumes unless
-    ``per_child_elems`` (meshing.py:375-454).  Current sources pass through unchanged; any other
-    object raises the reference's TypeError (supported here: Cuboid)."""
-    supported = (Cuboid,)
-    allowed = (*supported, BaseCurrent)
-    if not inplace:
-        obj = obj.copy(**kwargs)
-    children = [obj]
-    if isinstance(obj, Collection):
-        children = list(obj.sources_all)
-    incompatible_objs = [c for c in children if not isinstance(c, allowed)]
-    supported_objs = [c for c in children if isinstance(c, supported)]
-    if not per_child_elems:
-        volumes = np.array([get_volume(c) for c in supported_objs], dtype=float)
-        volumes /= volumes.sum()
-        target_elems_by_child = (volumes * target_elems).astype(int)
-        target_elems_by_child[target_elems_by_child < min_elems] = min_elems
-    else:
-        target_elems_by_child = [max(min_elems, target_elems)] * len(supported_objs)
-    if incompatible_objs:
-        counts_incompatible = Counter(s.__class__.__name__ for s in incompatible_objs)
-        counts_str = ", ".join(f"{count} {name}" for name, count in counts_incompatible.items())
-        msg = (
-            "Incompatible objects found: "
-            f"{counts_str}"
-            f"\nSupported: {[s.__name__ for s in supported]}."
-        )
+    """Mesh every Cuboid below ``obj`` (a single object or a Collection tree) and put the meshed
+    Collection in its place (meshing.py:375-454).  ``target_elems`` is shared among the cuboids by
+    volume unless ``per_child_elems``; current sources stay as they are; anything else raises the
+    reference's TypeError (the B200 path supports Cuboid magnets)."""
+    meshable = (Cuboid,)
+    root = obj if inplace else obj.copy(**kwargs)
+    leaves = list(root.sources_all) if isinstance(root, Collection) else [root]
+    cuboids = [c for c in leaves if isinstance(c, meshable)]
+    quota = _share_elements(cuboids, target_elems, min_elems, per_child_elems) if cuboids else []
+    rejected = Counter(type(c).__name__ for c in leaves if not isinstance(c, (*meshable, BaseCurrent)))
+    if rejected:
+        listing = ", ".join(f"{cnt} {name}" for name, cnt in rejected.items())
+        msg = f"Incompatible objects found: {listing}\nSupported: {[c.__name__ for c in meshable]}."
         raise TypeError(msg)
-    for child, targ_elems in zip(supported_objs, target_elems_by_child, strict=True):
-        parent = child.parent
-        kw = kwargs if parent is None else {}
-        child_meshed = mesh_Cuboid(child, int(targ_elems), **kw)
-        child.parent = None
-        if parent is not None:
-            parent.add(child_meshed)
+    for cub, n_cells in zip(cuboids, quota, strict=True):
+        owner = cub.parent
+        meshed = mesh_Cuboid(cub, n_cells, **({} if owner is not None else kwargs))
+        cub.parent = None  # detach the original; its meshed stand-in takes its place
+        if owner is None:
+            root = meshed
         else:
-            obj = child_meshed
-    return obj
+            owner.add(meshed)
+    return root

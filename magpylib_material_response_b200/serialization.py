@@ -1,15 +1,19 @@
 """JSON persistence of (solved) collections -- the reference's answer to "do not recompute the
-demagnetization" (/root/reference/src/magpylib_material_response/utils.py:110-271, format in
-docs/serialization.md).  Same document format, same type tags, same
-errors and warnings; the classes are whatever ``_compat`` provides (real magpylib objects when
-importable, the local stand-ins otherwise).  Cylinder / CylinderSegment tags are accepted only
-when magpylib supplies those classes.
+demagnetization" (/root/reference/src/magpylib_material_response/utils.py:110-271, document format in
+docs/serialization.md).
+
+The document format, type tags, units, error messages and warnings are the reference's; the
+implementation is table-driven: every type tag maps to its class and to the list of
+``(json key, attribute, unit)`` fields it carries besides the common pose/style block.  The classes
+are whatever ``_compat`` provides (real magpylib objects when importable, the local stand-ins
+otherwise); the Cylinder / CylinderSegment tags exist only when magpylib supplies those classes.
 """
 
 from __future__ import annotations
 
 import json
 import warnings
+from typing import NamedTuple
 
 import numpy as np
 from scipy.spatial.transform import Rotation
@@ -17,68 +21,82 @@ from scipy.spatial.transform import Rotation
 from . import _compat
 from ._compat import BaseCurrent, BaseMagnet, Circle, Collection, Cuboid, Polyline, Sensor
 
-# Type-tag <-> class mapping (utils.py:244-256).
-_CLASS_BY_TYPE = {
-    "magnet.Cuboid": Cuboid,
-    "current.Polyline": Polyline,
-    "current.Circle": Circle,
-    "Sensor": Sensor,
-    "Collection": Collection,
+
+class _Field(NamedTuple):
+    key: str        # key in the JSON object and constructor keyword
+    label: str      # name used in the unit error message
+    unit: str
+    scalar: bool = False
+    optional: bool = False
+
+
+class _Kind(NamedTuple):
+    cls: type
+    fields: tuple
+
+
+_POLARIZATION = _Field("polarization", "Polarization", "T")
+_CURRENT = _Field("current", "Current", "A", scalar=True)
+
+# type tag -> class and type-specific fields (utils.py:244-256 for the tags)
+_KINDS = {
+    "magnet.Cuboid": _Kind(Cuboid, (_POLARIZATION, _Field("dimension", "Dimension", "m"))),
+    "current.Polyline": _Kind(Polyline, (_CURRENT, _Field("vertices", "Vertices", "m"))),
+    "current.Circle": _Kind(Circle, (_CURRENT, _Field("diameter", "Diameter", "m", scalar=True))),
+    "Sensor": _Kind(Sensor, (_Field("pixel", "Pixel", "m", optional=True),)),
+    "Collection": _Kind(Collection, ()),
 }
 if _compat.HAVE_MAGPYLIB:  # pragma: no cover - magpylib is absent in the build/GPU image
     import magpylib as _magpy
 
-    _CLASS_BY_TYPE["magnet.Cylinder"] = _magpy.magnet.Cylinder
-    _CLASS_BY_TYPE["magnet.CylinderSegment"] = _magpy.magnet.CylinderSegment
-_TYPE_BY_CLASS = {cls: tag for tag, cls in _CLASS_BY_TYPE.items()}
+    _KINDS["magnet.Cylinder"] = _Kind(_magpy.magnet.Cylinder, (_POLARIZATION, _Field("dimension", "Dimension", "m")))
+    _KINDS["magnet.CylinderSegment"] = _Kind(
+        _magpy.magnet.CylinderSegment, (_POLARIZATION, _Field("dimension", "Dimension", "m,m,m,deg,deg")))
+_TAG_OF = {kind.cls: tag for tag, kind in _KINDS.items()}
+# the reference's private names, kept for callers that import them
+_CLASS_BY_TYPE = {tag: kind.cls for tag, kind in _KINDS.items()}
+_TYPE_BY_CLASS = _TAG_OF
 
 
-def _rotation_matrix(obj):
-    return obj.orientation.as_matrix().tolist()
+def _plain(value, scalar):
+    """numpy / python value -> JSON primitive(s); missing excitations serialize as zero."""
+    if scalar:
+        return float(0.0 if value is None else value)
+    return np.asarray((0.0, 0.0, 0.0) if value is None else value, dtype=float).tolist()
 
 
 def _serialize_recursive(obj, parent="warn"):
-    """Object -> JSON-compatible dict (utils.py:110-173)."""
-    typ = _TYPE_BY_CLASS.get(type(obj))
-    if typ is None:
+    """Object -> JSON-compatible dict with a namespaced ``type`` tag (utils.py:110-173)."""
+    tag = _TAG_OF.get(type(obj))
+    if tag is None:
         msg = (
             f"Unsupported object type: {obj.__class__.__name__!r}. "
-            f"Supported types: {sorted(_CLASS_BY_TYPE)}"
+            f"Supported types: {sorted(_KINDS)}"
         )
         raise TypeError(msg)
-    dd = {
-        "type": typ,
+    if parent == "warn" and obj.parent is not None:
+        warnings.warn(f"object parent ({obj.parent}) not included in serialization", stacklevel=2)
+    doc = {
+        "type": tag,
         "position": {"value": np.asarray(obj.position).tolist(), "unit": "m"},
-        "orientation": {"value": _rotation_matrix(obj), "representation": "matrix"},
+        "orientation": {"value": obj.orientation.as_matrix().tolist(), "representation": "matrix"},
     }
     style = obj.style.as_dict()
     if style:
-        dd["style"] = style
-    if parent == "warn" and obj.parent is not None:
-        warnings.warn(f"object parent ({obj.parent}) not included in serialization", stacklevel=2)
+        doc["style"] = style
+    for fld in _KINDS[tag].fields:
+        value = getattr(obj, fld.key)
+        if fld.optional and value is None:
+            continue
+        doc[fld.key] = {"value": _plain(value, fld.scalar), "unit": fld.unit}
     if isinstance(obj, BaseMagnet):
-        pol = (0.0, 0.0, 0.0) if obj.polarization is None else obj.polarization
-        dd["polarization"] = {"value": np.asarray(pol, dtype=float).tolist(), "unit": "T"}
-        susceptibility = getattr(obj, "susceptibility", None)
-        if susceptibility is not None:
-            sus = np.asarray(susceptibility)
-            dd["susceptibility"] = {"value": sus.tolist() if sus.ndim else float(sus)}
-    if isinstance(obj, BaseCurrent):
-        dd["current"] = {"value": float(0.0 if obj.current is None else obj.current), "unit": "A"}
-    if typ in ("magnet.Cuboid", "magnet.Cylinder"):
-        dd["dimension"] = {"value": np.asarray(obj.dimension).tolist(), "unit": "m"}
-    elif typ == "magnet.CylinderSegment":
-        dd["dimension"] = {"value": np.asarray(obj.dimension).tolist(), "unit": "m,m,m,deg,deg"}
-    elif typ == "current.Polyline":
-        dd["vertices"] = {"value": np.asarray(obj.vertices).tolist(), "unit": "m"}
-    elif typ == "current.Circle":
-        dd["diameter"] = {"value": float(obj.diameter), "unit": "m"}
-    elif typ == "Sensor":
-        if obj.pixel is not None:
-            dd["pixel"] = {"value": np.asarray(obj.pixel).tolist(), "unit": "m"}
-    elif typ == "Collection":
-        dd["children"] = [_serialize_recursive(child, parent="ignore") for child in obj.children]
-    return dd
+        chi = getattr(obj, "susceptibility", None)
+        if chi is not None:
+            chi = np.asarray(chi)
+            doc["susceptibility"] = {"value": chi.tolist() if chi.ndim else float(chi)}
+    if tag == "Collection":
+        doc["children"] = [_serialize_recursive(child, parent="ignore") for child in obj.children]
+    return doc
 
 
 def _check_unit(field_name, inp, expected):
@@ -90,50 +108,34 @@ def _check_unit(field_name, inp, expected):
 
 def _deserialize_recursive(inp):
     """Inverse of :func:`_serialize_recursive` (utils.py:183-241)."""
-    typ = inp.get("type")
-    constr = _CLASS_BY_TYPE.get(typ)
-    if constr is None:
-        msg = f"Unknown type tag {typ!r}. Supported tags: {sorted(_CLASS_BY_TYPE)}"
+    tag = inp.get("type")
+    kind = _KINDS.get(tag)
+    if kind is None:
+        msg = f"Unknown type tag {tag!r}. Supported tags: {sorted(_KINDS)}"
         raise TypeError(msg)
-    kw = {}
     _check_unit("Position", inp["position"], "m")
-    kw["position"] = inp["position"]["value"]
-    rep = inp["orientation"].get("representation")
-    if rep != "matrix":
-        msg = f"Orientation representation must be 'matrix', got {rep!r}"
+    representation = inp["orientation"].get("representation")
+    if representation != "matrix":
+        msg = f"Orientation representation must be 'matrix', got {representation!r}"
         raise ValueError(msg)
-    kw["orientation"] = Rotation.from_matrix(inp["orientation"]["value"])
-    style = inp.get("style")
-    if style is not None:
-        kw["style"] = style
+    kwargs = {
+        "position": inp["position"]["value"],
+        "orientation": Rotation.from_matrix(inp["orientation"]["value"]),
+    }
+    if inp.get("style") is not None:
+        kwargs["style"] = inp["style"]
     if inp.get("parent") is not None:
         warnings.warn(f"object parent ({inp['parent']}) ignored", stacklevel=2)
-    if issubclass(constr, BaseMagnet):
-        _check_unit("Polarization", inp["polarization"], "T")
-        kw["polarization"] = inp["polarization"]["value"]
-    if issubclass(constr, BaseCurrent):
-        _check_unit("Current", inp["current"], "A")
-        kw["current"] = inp["current"]["value"]
-    if typ in ("magnet.Cuboid", "magnet.Cylinder"):
-        _check_unit("Dimension", inp["dimension"], "m")
-        kw["dimension"] = inp["dimension"]["value"]
-    elif typ == "magnet.CylinderSegment":
-        _check_unit("Dimension", inp["dimension"], "m,m,m,deg,deg")
-        kw["dimension"] = inp["dimension"]["value"]
-    elif typ == "current.Polyline":
-        _check_unit("Vertices", inp["vertices"], "m")
-        kw["vertices"] = inp["vertices"]["value"]
-    elif typ == "current.Circle":
-        _check_unit("Diameter", inp["diameter"], "m")
-        kw["diameter"] = inp["diameter"]["value"]
-    elif typ == "Sensor" and "pixel" in inp:
-        _check_unit("Pixel", inp["pixel"], "m")
-        kw["pixel"] = inp["pixel"]["value"]
-    obj = constr(**kw)
+    for fld in kind.fields:
+        if fld.optional and fld.key not in inp:
+            continue
+        _check_unit(fld.label, inp[fld.key], fld.unit)
+        kwargs[fld.key] = inp[fld.key]["value"]
+    obj = kind.cls(**kwargs)
     if inp.get("susceptibility") is not None:
-        sus = inp["susceptibility"]["value"]
-        obj.susceptibility = tuple(sus) if isinstance(sus, list) else sus
-    if typ == "Collection":
+        chi = inp["susceptibility"]["value"]
+        obj.susceptibility = tuple(chi) if isinstance(chi, list) else chi
+    if tag == "Collection":
         obj.add(*[_deserialize_recursive(child) for child in inp["children"]])
     return obj
 
