@@ -319,10 +319,26 @@ def _rotate_rows(src_list, vecs, inverse=False):
     return rot.apply(vecs, inverse=inverse)
 
 
+def _system_key(pos, quat, dim, chi, max_dist, solver):
+    """Fingerprint of everything the system matrix depends on (bit-exact geometry, chi, max_dist)."""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=20)
+    for a in (pos, quat, dim, chi):
+        h.update(np.ascontiguousarray(a, dtype=float).tobytes())
+    h.update(np.float64(max_dist).tobytes())
+    return f"{solver}:{len(pos)}:{h.hexdigest()}"
+
+
 def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching=False, max_dist=0,
-                       split=1, solver="lu", tol=1e-12, device=None, min_log_time=None):
+                       split=1, solver="lu", tol=1e-12, device=None, min_log_time=None, demag_store=None):
     """Host arrays in, host array out: assemble Q = I - chi*N on the device, solve
-    Q x = J0 + chi*H_ext (demag.py:444-470).  All (n,3) arrays, GLOBAL frame.  Returns (x, info)."""
+    Q x = J0 + chi*H_ext (demag.py:444-470).  All (n,3) arrays, GLOBAL frame.  Returns (x, info).
+
+    ``demag_store`` (a dict, single GPU): the device-resident system of this geometry -- the LU
+    factors and pivots for ``solver="lu"``, the assembled Q for ``"gmres"`` -- is kept in it and
+    reused by later calls with bit-identical cells, chi and max_dist, which then only pay for the
+    right-hand side (triangular solves: milliseconds instead of the O(n^3) factorization)."""
     from . import distributed as mdist
 
     ctx = _native.default_context(device)
@@ -362,24 +378,39 @@ def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching
         info["n_gpus"] = ctx.nranks
         return x, info
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    key = None if demag_store is None else _system_key(pos, quat, dim, chi, max_dist, solver)
+    cached = None if key is None else demag_store.get(key)
+    if cached is not None and cached["device"] != str(ctx.device):
+        cached = None
+    info["demag_store"] = None if demag_store is None else ("hit" if cached is not None else "miss")
     ev[0].record(ctx.stream)
     with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):
-        Q, ld = _assemble_device(
-            ctx, pos, quat, dim, chi_cell_major=np.asarray(chi, dtype=float).reshape(N),
-            pairs_matching=pairs_matching, max_dist=max_dist, split=split,
-        )
+        if cached is not None:
+            Q, ld = cached["Q"], cached["ld"]
+        else:
+            Q, ld = _assemble_device(
+                ctx, pos, quat, dim, chi_cell_major=np.asarray(chi, dtype=float).reshape(N),
+                pairs_matching=pairs_matching, max_dist=max_dist, split=split,
+            )
     ev[1].record(ctx.stream)
     with timelog("Solving of linear system", min_log_time=min_log_time):
         d_x = ctx.to_device(rhs)
         if solver == "lu":
-            ipiv = ctx.empty(N, dtype=torch.int32)
-            lu_info = ctx.lu_factor(Q, ld, ipiv)
-            if lu_info != 0:
-                msg = f"Singular matrix (zero pivot at elimination step {lu_info})"
-                raise np.linalg.LinAlgError(msg)
+            if cached is not None:
+                ipiv = cached["ipiv"]
+            else:
+                ipiv = ctx.empty(N, dtype=torch.int32)
+                lu_info = ctx.lu_factor(Q, ld, ipiv)
+                if lu_info != 0:
+                    msg = f"Singular matrix (zero pivot at elimination step {lu_info})"
+                    raise np.linalg.LinAlgError(msg)
+                if key is not None:
+                    demag_store[key] = {"Q": Q, "ld": ld, "ipiv": ipiv, "device": str(ctx.device)}
             ev[2].record(ctx.stream)
             ctx.lu_solve(Q, ld, ipiv, d_x)
         else:
+            if key is not None and cached is None:
+                demag_store[key] = {"Q": Q, "ld": ld, "device": str(ctx.device)}
             d_b = d_x
             d_x = d_b.clone()
             ev[2].record(ctx.stream)
@@ -394,7 +425,7 @@ def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching
 
 
 def apply_demag_arrays(pos, quat, dim, pol, chi, H_ext=None, *, pairs_matching=False, max_dist=0, split=1,
-                       solver="lu", tol=1e-12, device=None, return_info=False):
+                       solver="lu", tol=1e-12, device=None, return_info=False, demag_store=None):
     """Array-level form of ``apply_demag`` (structure-of-arrays in host memory, no objects):
     pos (n,3), quat (n,4) scalar-last, dim (n,3), pol (n,3) LOCAL-frame polarizations, chi scalar /
     (3,) / (n,) / (n,3), H_ext (n,3) or (3,).  Returns the solved LOCAL-frame polarizations (n,3).
@@ -418,7 +449,8 @@ def apply_demag_arrays(pos, quat, dim, pol, chi, H_ext=None, *, pairs_matching=F
         return (np.zeros((0, 3)), {}) if return_info else np.zeros((0, 3))
     rot = R.from_quat(quat)
     x, info = solve_cells_global(pos, quat, dim, rot.apply(pol), chi_a, H, pairs_matching=pairs_matching,
-                                 max_dist=max_dist, split=split, solver=solver, tol=tol, device=device)
+                                 max_dist=max_dist, split=split, solver=solver, tol=tol, device=device,
+                                 demag_store=demag_store)
     out = rot.apply(x, inverse=True)
     return (out, info) if return_info else out
 
@@ -446,9 +478,14 @@ def apply_demag(
     partial pivoting on FP64 tensor cores, default, the np.linalg.solve equivalent) or "gmres"
     (restarted GMRES with true-residual check, relative tolerance ``tol``); ``device`` CUDA
     index; ``return_info`` also returns a dict with per-stage device timings.
-    ``demag_store`` (named by the north star, absent from the reference) is accepted and ignored.
+    ``demag_store`` (named by the north star, absent from the reference): ``None`` or a dict in which the
+    device-resident factorized system of this geometry is kept; later calls with the same cells,
+    susceptibilities and ``max_dist`` -- e.g. a sweep over ``H_ext``, polarizations or coil currents --
+    reuse it and only run the triangular solves (single GPU; see ``solve_cells_global``).
     """
-    del demag_store
+    if demag_store is not None and not hasattr(demag_store, "get"):
+        msg = "demag_store must be None or a dict-like mapping"
+        raise TypeError(msg)
     if solver not in ("lu", "gmres"):
         msg = "solver must be 'lu' or 'gmres'"
         raise ValueError(msg)
@@ -522,6 +559,7 @@ def apply_demag(
         pol_new, solve_info = solve_cells_global(
             pos, quat, dim, pol_global, chi, H_ext, pairs_matching=pairs_matching, max_dist=max_dist,
             split=split, solver=solver, tol=tol, device=device, min_log_time=min_log_time,
+            demag_store=demag_store,
         )
         info.update(solve_info)
 

@@ -513,6 +513,48 @@ def test_config5_magnet_array_max_dist_split_reduced_vs_oracle():
         assert np.max(np.abs(got - ref) / scale) <= J_RTOL, (solver, split)
 
 
+@pytest.mark.parametrize("solver", ["lu", "gmres"])
+def test_demag_store_reuses_the_factorized_system(solver):
+    """demag_store (north-star keyword): the second call on the same cells / chi only changes the
+    right-hand side -- it must hit the store, skip assembly + factorization and still match the oracle."""
+    from bench import make_workload
+
+    w = make_workload("two_magnets_432")
+    store = {}
+    kw = dict(solver=solver, tol=1e-13, return_info=True, demag_store=store)
+    x1, info1 = mmr.demag.apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw)
+    assert info1["demag_store"] == "miss" and len(store) == 1
+    rng = np.random.default_rng(3)
+    pol2 = rng.normal(size=w["pol"].shape)
+    H2 = rng.normal(size=w["H_ext"].shape) * 0.1
+    x2, info2 = mmr.demag.apply_demag_arrays(w["pos"], w["quat"], w["dim"], pol2, w["chi"], H2, **kw)
+    assert info2["demag_store"] == "hit" and len(store) == 1
+    assert info2["assemble_ms"] < 0.5 * info1["assemble_ms"]
+    for x, pol, H in ((x1, w["pol"], w["H_ext"]), (x2, pol2, H2)):
+        ref = oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], pol, w["chi"], H_ext=H)
+        assert np.max(np.abs(x - ref) / np.abs(ref).max(axis=1, keepdims=True)) <= J_RTOL
+    # a different chi is a different system
+    chi3 = w["chi"] * 1.5
+    _, info3 = mmr.demag.apply_demag_arrays(w["pos"], w["quat"], w["dim"], pol2, chi3, H2, **kw)
+    assert info3["demag_store"] == "miss" and len(store) == 2
+
+
+def test_demag_store_through_the_object_api():
+    cube = Cuboid(polarization=(0, 0, 0), dimension=(1e-3, 1e-3, 2e-3))
+    cube.susceptibility = 80.0
+    mesh = mesh_Cuboid(cube, 96)
+    store = {}
+    outs = []
+    for hz in (0.1, 0.2):
+        mesh.H_ext = (0, 0, hz)
+        out, info = apply_demag(mesh, demag_store=store, return_info=True)
+        outs.append(np.array([s.polarization for s in out.sources_all]))
+    assert info["demag_store"] == "hit" and len(store) == 1
+    np.testing.assert_allclose(outs[1], 2.0 * outs[0], rtol=1e-10)  # linear in the excitation
+    with pytest.raises(TypeError, match="demag_store must be None or a dict-like mapping"):
+        apply_demag(mesh, demag_store=42)
+
+
 def test_config2prime_8000_cells_properties(ctx):
     """North-star target config: soft-iron cube 20x20x20, chi=1000, H_ext=(0,0,1)."""
     cube = Cuboid(dimension=(1e-3,) * 3, polarization=(0, 0, 0))
