@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mmr_b200.h"
@@ -45,6 +46,11 @@ struct mmr_ctx {
   cudaStream_t side = nullptr;
   bool lookahead = true;
   void* laswp_buf = nullptr;  // LaswpPerm scratch (lu.cu)
+  // kernel attributes are per device: what this context has already raised / probed (never process-wide
+  // statics, so that contexts on several devices of one process work)
+  std::unordered_map<const void*, size_t> func_smem;  // MaxDynamicSharedMemorySize set so far, per kernel
+  int panel_cluster_max = -1;                          // largest launchable strip cluster (-1: not probed)
+  bool panel_reg_ok = false;                           // non-portable cluster sizes allowed for the register strips
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -87,6 +93,8 @@ struct DeviceGuard {
 int mmr_ws_reserve(mmr_ctx* ctx, size_t bytes);    // ctx->ws
 int mmr_ws2_reserve(mmr_ctx* ctx, size_t bytes);   // ctx->ws2
 int mmr_hpin_reserve(mmr_ctx* ctx, size_t bytes);  // ctx->hpin
+// raise a kernel's dynamic shared-memory limit to `bytes` on this context's device (once per size)
+int mmr_func_smem(mmr_ctx* ctx, const void* func, size_t bytes);
 
 // profiling scope: records an event pair around the launches enqueued in between
 int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s);

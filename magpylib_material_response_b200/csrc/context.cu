@@ -40,6 +40,15 @@ int mmr_ws2_reserve(mmr_ctx* ctx, size_t bytes) {
   if (ctx->ws2_bytes < bytes && ctx->ws2) cudaStreamSynchronize(ctx->stream);
   return reserve(&ctx->ws2, &ctx->ws2_bytes, bytes, false);
 }
+int mmr_func_smem(mmr_ctx* ctx, const void* func, size_t bytes) {
+  size_t& have = ctx->func_smem[func];
+  if (bytes > have) {
+    MMR_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
+}
+
 int mmr_hpin_reserve(mmr_ctx* ctx, size_t bytes) {
   if (ctx->hpin_bytes < bytes && ctx->hpin) cudaStreamSynchronize(ctx->stream);
   return reserve(&ctx->hpin, &ctx->hpin_bytes, bytes, true);

@@ -143,10 +143,9 @@ extern "C" int mmr_field_currents(mmr_ctx* ctx, int64_t m, const double* d_obs, 
   MMR_ARG(d_obs && d_out && (d_seg || nseg == 0) && (d_loop || nloop == 0), "NULL pointer");
   DeviceGuard g(ctx->device);
   const size_t smem = sizeof(double) * (size_t)(7 * nseg + 9 * nloop);
-  static size_t cap = 48 * 1024;
-  if (smem > cap) {
-    MMR_CUDA(cudaFuncSetAttribute(current_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cap = smem;
+  if (smem > 48 * 1024) {
+    const int rc = mmr_func_smem(ctx, (const void*)current_field_kernel, smem);
+    if (rc) return rc;
   }
   // B = mu0/(4 pi) * (...);  H = B / mu0 = (...) / (4 pi) outside the (infinitely thin) conductor
   const double scale = (field == MMR_FIELD_B) ? MU0_4PI : 1.0 / (4.0 * PI);

@@ -805,21 +805,18 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
                          double*, int64_t);
   static const kern_t kerns[4] = {dgemm_nn_kernel<false, false>, dgemm_nn_kernel<false, true>,
                                   dgemm_nn_kernel<true, false>, dgemm_nn_kernel<true, true>};
-  static bool attr_set[4] = {false, false, false, false};
   const int which = (aligned ? 2 : 0) + (subtract ? 1 : 0);
-  if (!attr_set[which]) {
-    MMR_CUDA(cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set[which] = true;
-  }
+  int arc = mmr_func_smem(ctx, (const void*)kerns[which], SMEM_BYTES);
+  if (arc) return arc;
   dim3 grid((unsigned)ceil_div64(m, BM), (unsigned)ceil_div64(n, BN));
   const int64_t ntiles = (int64_t)grid.x * grid.y;
   static int fast = -1;
   if (fast < 0) {
     const char* e = getenv("MMR_DGEMM_FAST");
     fast = (e && e[0] == '0') ? 0 : 1;
-    MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MMR_CUDA(cudaFuncSetAttribute(dgemm_nn_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
+  if ((arc = mmr_func_smem(ctx, (const void*)dgemm_nn_fast_kernel<true>, SMEM_BYTES))) return arc;
+  if ((arc = mmr_func_smem(ctx, (const void*)dgemm_nn_fast_kernel<false>, SMEM_BYTES))) return arc;
   static int prefetch_on = -1;
   if (prefetch_on < 0) {
     const char* e = getenv("MMR_DGEMM_PREFETCH");
@@ -855,20 +852,14 @@ extern "C" int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, doubl
 // into d_ipiv[kb..kb+nb) (global row indices).  Used by the single-GPU and distributed drivers.
 int mmr_lu_panel(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
                  int* d_info, void* d_scratch) {
-  static int max_coop_ctas = -1;
-  static size_t strip_smem_cap = 0;
-  if (max_coop_ctas < 0) {
-    strip_smem_cap = 200 * 1024;
-    MMR_CUDA(cudaFuncSetAttribute(lu_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)strip_smem_cap));
-    max_coop_ctas = ctx->sm_count;  // 1 CTA per SM at up to 200 KB of shared memory
-  }
-  static bool reg_ok = false;
-  static int cluster_max = -1;  // largest launchable cluster size for the cluster strip kernel
-  if (cluster_max < 0) {
-    cluster_max = 0;
-    if (cudaFuncSetAttribute(lu_strip_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)strip_smem_cap) == cudaSuccess &&
+  // capabilities of this context's device, probed once per context
+  const size_t strip_smem_cap = 200 * 1024;
+  const int max_coop_ctas = ctx->sm_count;  // 1 CTA per SM at up to 200 KB of shared memory
+  if (ctx->panel_cluster_max < 0) {
+    int rc0 = mmr_func_smem(ctx, (const void*)lu_strip_kernel, strip_smem_cap);
+    if (rc0) return rc0;
+    int found = 0;  // largest launchable cluster size for the cluster strip kernel
+    if (mmr_func_smem(ctx, (const void*)lu_strip_cluster_kernel, strip_smem_cap) == 0 &&
         cudaFuncSetAttribute(lu_strip_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) ==
             cudaSuccess) {
       for (int cs = 16; cs >= 1; cs >>= 1) {
@@ -886,17 +877,21 @@ int mmr_lu_panel(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, 
         int nclusters = 0;
         if (cudaOccupancyMaxActiveClusters(&nclusters, lu_strip_cluster_kernel, &cfg) == cudaSuccess &&
             nclusters >= 1) {
-          cluster_max = cs;
+          found = cs;
           break;
         }
       }
     }
     cudaGetLastError();  // clear any probe error
-    reg_ok = cudaFuncSetAttribute(lu_strip_reg_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-             cudaFuncSetAttribute(lu_strip_reg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-             cudaFuncSetAttribute(lu_strip_reg_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    ctx->panel_reg_ok =
+        cudaFuncSetAttribute(lu_strip_reg_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(lu_strip_reg_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(lu_strip_reg_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     cudaGetLastError();
+    ctx->panel_cluster_max = found;
   }
+  const int cluster_max = ctx->panel_cluster_max;
+  const bool reg_ok = ctx->panel_reg_ok;
   Cand* cand = (Cand*)d_scratch;
   double* candrow = (double*)((char*)d_scratch + 2 * 256 * sizeof(Cand));
   double* diagrow = candrow + 2 * 256 * W;
@@ -1268,11 +1263,10 @@ size_t mmr_lu_spec_scratch_bytes() { return sizeof(double) * NB * NB + 256; }  /
 // result; 0: nothing was modified (the caller runs the pivoting path).  Synchronises `strm`.
 int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
                       double* S, double* Linv, void* d_spec, int* ok_out) {
-  static bool attr = false;
   const size_t inv_smem = ((size_t)TINV_COLS * (NB + 1) + (size_t)NB * (NB + 1)) * sizeof(double);
-  if (!attr) {
-    MMR_CUDA(cudaFuncSetAttribute(lu_tri_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
-    attr = true;
+  {
+    const int rc0 = mmr_func_smem(ctx, (const void*)lu_tri_inv_kernel, inv_smem);
+    if (rc0) return rc0;
   }
   static int seg = -1;
   if (seg < 0) {
@@ -1479,10 +1473,9 @@ int mmr_lu_laswp(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int k0,
 int mmr_lu_trsm(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, int nb, double* B, int64_t ldb, int ncols) {
   if (ncols <= 0 || nb <= 0) return 0;
   const size_t smem = ((size_t)TRSM_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
-  static size_t cap = 0;
-  if (smem > cap) {
-    MMR_CUDA(cudaFuncSetAttribute(lu_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cap = smem;
+  {
+    const int rc0 = mmr_func_smem(ctx, (const void*)lu_trsm_kernel, smem);
+    if (rc0) return rc0;
   }
   lu_trsm_kernel<<<(unsigned)ceil_div64(ncols, TRSM_COLS), 256, smem, strm>>>(L, ldl, nb, B, ldb, ncols);
   MMR_CHECK_LAUNCH(ctx);
@@ -1661,13 +1654,10 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
 // as soon as a diagonal block of the solution is final it is eliminated from ALL remaining
 // equations at once (one warp per remaining column, SB-long contiguous dot products).
 int mmr_lu_tri_solves(mmr_ctx* ctx, int N, const double* A, int64_t ld, double* d_b) {
-  static bool attr = false;
   const size_t smem = (size_t)SB * (SB + 1) * sizeof(double);
-  if (!attr) {
-    MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  int arc = mmr_func_smem(ctx, (const void*)lu_diag_solve_kernel<true>, smem);
+  if (arc) return arc;
+  if ((arc = mmr_func_smem(ctx, (const void*)lu_diag_solve_kernel<false>, smem))) return arc;
   for (int k0 = 0; k0 < N; k0 += SB) {
     const int k1 = min(N, k0 + SB);
     lu_diag_solve_kernel<true><<<1, DIAG_THREADS, smem, ctx->stream>>>(A, ld, k0, k1, N, d_b);
@@ -1981,8 +1971,8 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
 
   // ---- triangular solves, block by block (each block in two <= 128-row steps) -----------------
   const size_t diag_smem = (size_t)SB * (SB + 1) * sizeof(double);
-  MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
-  MMR_CUDA(cudaFuncSetAttribute(lu_diag_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
+  if ((rc = mmr_func_smem(ctx, (const void*)lu_diag_solve_kernel<true>, diag_smem))) return rc;
+  if ((rc = mmr_func_smem(ctx, (const void*)lu_diag_solve_kernel<false>, diag_smem))) return rc;
   for (int s = 0; s < S; ++s) {  // U^T w = b
     const int kb = s * obw, ob = min(obw, N - kb), owner = s % R;
     const int nb0 = min(NB, ob), nb1 = ob - nb0;
