@@ -200,10 +200,14 @@ int mmr_gmres_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_blo
                    double tol, int restart, int maxit, int* iters_out, double* relres_out);
 
 /*
- * Distributed LU + solve: 1-D block-cyclic over row blocks of Q (= column panels of Q^T) of
- * width 3*tgt_block; panel factorization is local to the owner, the factored panel and its
- * pivots are ncclBroadcast, every rank swaps and updates its own panels.  d_b (N, replicated)
- * is overwritten by the solution on every rank.
+ * Distributed LU + solve: 1-D block-cyclic over row blocks of Q (= column blocks of Q^T) of
+ * width 3*tgt_block <= 256 (one block = up to two 128-column LU panels = one rank-3*tgt_block
+ * DMMA update; 3*tgt_block a multiple of 16, e.g. tgt_block = 80, keeps the fast GEMM kernel).
+ * The block factorization is local to its owner; the packed block, both inverted diagonal blocks
+ * and the pivots travel as ONE ncclBroadcast per block on the context's side stream, overlapped
+ * with the update by the previous block; every rank swaps and updates its own trailing blocks.
+ * d_b (N, replicated) is overwritten by the solution on every rank.  *info_out > 0: zero pivot
+ * seen by THIS rank (reduce over ranks with max).
  */
 int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block,
                       double* d_Qlocal, int64_t ld, double* d_b, int* info_out);
