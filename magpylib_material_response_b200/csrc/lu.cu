@@ -994,7 +994,7 @@ size_t mmr_lu_panel_scratch_bytes() { return 2 * 256 * sizeof(Cand) + (2 * 256 *
 // Speculative panel: "the pivot is on the diagonal" (true for the demag matrices Q = I - chi*T
 // of every BASELINE config), verified a posteriori.
 //
-//   1. lu_diag_nopiv_kernel   LU without interchanges of the nb x nb diagonal block (one CTA)
+//   1. lu_diag_nopiv_tile_kernel  LU without interchanges of the nb x nb diagonal block (one CTA)
 //   2. lu_tri_inv_kernel      L11^-1 and U11^-1                                   (8 CTAs)
 //   3. DMMA GEMM              L21 = A21 * U11^-1                                   (all SMs)
 //   4. lu_spec_check / commit max |l_ij| <= 1 ?  then copy the packed panel into A, ipiv = identity
@@ -1020,104 +1020,103 @@ __device__ __forceinline__ double fast_rcp(double a) {
   x = fma(x, fma(-a, x, 1.0), x);
   return x;
 }
-__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// Thread (r, q) owns row r, columns [q*SEG, (q+1)*SEG) in registers.  The 128 steps run in NQ
-// phases of SEG steps; in phase p segment p is the pivot segment (its SEG steps are fully unrolled:
-// every register index is static, finished columns cost nothing), segments q > p apply each step
-// one barrier interval later (they need the multiplier column the pivot segment publishes), and
-// segments q < p only keep the barrier count.  One CTA barrier per step.  Pivot row j+1 is
-// published by its owner thread right after it has applied step j; the reciprocal of the next
-// pivot is computed first so that it overlaps the rest of the update.
-template <int SEG>
-__global__ void __launch_bounds__(128 * (128 / SEG), 1)
-    lu_diag_nopiv_kernel(const double* __restrict__ A, int64_t ld, int kb, int nb, double* __restrict__ S,
-                         int64_t lds, int* __restrict__ flag) {
-  constexpr int NQ = 128 / SEG;
-  __shared__ __align__(16) double urow[NQ][2][SEG];
-  __shared__ __align__(16) double lcol[2][128];
-  __shared__ double s_rinv[2];
+// LU without interchanges of the nb x nb (<= 128) diagonal block in ONE CTA.  Warp w owns the columns
+// {w + 16 b}, lane t the rows {t + 32 a} -- 4 x 8 values per thread, the whole block lives in registers.
+// Step j needs no shared-memory traffic for the pivot
+// ROW at all (each warp broadcasts its own eight entries of row j from lane j % 32 with shuffles); only
+// the multiplier column, computed by the one warp that holds column j, goes through shared memory
+// (4 conflict-free stores, double buffered -> one CTA barrier per step).  All register indices are
+// static: the step loop is split into 8 blocks of 16 steps in which the register row (a = j / 32) and the
+// register column (b = j / 16) of the pivot are compile-time constants, and finished register rows /
+// columns drop out of the unrolled update.  The reciprocal of the next pivot is computed by the lane that
+// owns it right after its update.  Per step the critical path is the recurrence pivot -> reciprocal
+// (MUFU.RCP64H + 2 Newton steps) -> multipliers -> update of the next pivot: ~0.4 us, 52 us per block.
+// (A first layout -- one row segment per thread, the pivot row published through shared memory by its
+// single owner thread -- measured the same 0.4 us per step with 30x more shared-memory stores.)
+__global__ void __launch_bounds__(512, 1)
+    lu_diag_nopiv_tile_kernel(const double* __restrict__ A, int64_t ld, int kb, int nb, double* __restrict__ S,
+                              int64_t lds, int* __restrict__ flag) {
+  __shared__ double lcol[2][128];
   __shared__ int s_bad;
-  const int tid = threadIdx.x, r = tid & 127, q = tid >> 7;
-  double v[SEG];
+  const int tid = threadIdx.x, tr = tid & 31, tc = tid >> 5;
+  double v[4][8];
 #pragma unroll
-  for (int c = 0; c < SEG; ++c) {
-    const int gc = q * SEG + c;
-    v[c] = (r < nb && gc < nb) ? A[(int64_t)(kb + gc) * ld + kb + r] : ((r == gc) ? 1.0 : 0.0);
-  }
-  if (tid == 0) {
-    s_bad = 0;
-    s_rinv[0] = fast_rcp(v[0]);
-  }
-  if (r == 0) {
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int c = 0; c < SEG; ++c) urow[q][0][c] = v[c];
-  }
-  cta_bar();
+    for (int b = 0; b < 8; ++b) {
+      const int r = tr + 32 * a, c = tc + 16 * b;
+      v[a][b] = (r < nb && c < nb) ? A[(int64_t)(kb + c) * ld + kb + r] : ((r == c) ? 1.0 : 0.0);
+    }
+  if (tid == 0) s_bad = 0;
+  double rinv_next = (tid == 0) ? fast_rcp(v[0][0]) : 0.0;  // lives in the lane that holds the next pivot
+  __syncthreads();
   bool bad = false;
+#pragma unroll
+  for (int aj = 0; aj < 4; ++aj) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int bj = 2 * aj + h;  // compile-time after unrolling
 #pragma unroll 1
-  for (int p = 0; p < NQ; ++p) {
-    if (q == p) {
+      for (int q = 0; q < 16; ++q) {
+        const int j = 32 * aj + 16 * h + q;  // pivot row: lane jl, register row aj; pivot column: warp q, register column bj
+        const int jl = 16 * h + q;
+        if (tc == q) {  // the warp that holds column j: multipliers
+          const double rinv = __shfl_sync(0xffffffffu, rinv_next, jl);
+          const double piv = __shfl_sync(0xffffffffu, v[aj][bj], jl);
+          if (piv == 0.0) bad = true;
 #pragma unroll
-      for (int i = 0; i <= SEG; ++i) {
-        if (i < SEG) {
-          const int j = p * SEG + i;
-          const double* u = urow[q][j & 1];
-          const double rinv = s_rinv[j & 1];
-          const bool act = r > j;
-          const double l = act ? v[i] * rinv : 0.0;
-          if (u[i] == 0.0 || (act && !(fabs(l) <= 1.0))) bad = true;
-          if (act) v[i] = l;
-          lcol[j & 1][r] = l;
-          if (i + 1 < SEG) {
-            v[i + 1] -= l * u[i + 1];
-            const double nrinv = fast_rcp(v[i + 1]);
-#pragma unroll
-            for (int c = i + 2; c < SEG; ++c) v[c] -= l * u[c];
-            if (r == j + 1) {
-              s_rinv[(j + 1) & 1] = nrinv;
-              double* un = urow[q][(j + 1) & 1];
-#pragma unroll
-              for (int c = i + 1; c < SEG; ++c) un[c] = v[c];
+          for (int a = 0; a < 4; ++a) {
+            const int r = tr + 32 * a;
+            double l = 0.0;
+            if (a >= aj && r > j) {
+              l = v[a][bj] * rinv;
+              if (!(fabs(l) <= 1.0)) bad = true;
+              v[a][bj] = l;
             }
+            lcol[j & 1][r] = l;
           }
         }
-        cta_bar();
-      }
-    } else if (q > p) {
+        __syncthreads();
+        double l[4];
 #pragma unroll
-      for (int i = 0; i <= SEG; ++i) {
-        if (i >= 1) {
-          const int j = p * SEG + i - 1;
-          const double* u = urow[q][j & 1];
-          const double l = lcol[j & 1][r];
-          v[0] -= l * u[0];
-          double nrinv = 0.0;
-          if (i == SEG && q == p + 1) nrinv = fast_rcp(v[0]);  // my segment is the next pivot segment
+        for (int a = 0; a < 4; ++a) l[a] = (a >= aj) ? lcol[j & 1][tr + 32 * a] : 0.0;
 #pragma unroll
-          for (int c = 1; c < SEG; ++c) v[c] -= l * u[c];
-          if (r == j + 1) {
-            if (i == SEG && q == p + 1) s_rinv[(j + 1) & 1] = nrinv;
-            double* un = urow[q][(j + 1) & 1];
+        for (int b = 0; b < 8; ++b) {
+          if (b < bj) continue;             // finished register columns (static)
+          if (b == bj && tc <= q) continue;  // column tc + 16 bj <= j (warp-uniform)
+          const double u = __shfl_sync(0xffffffffu, v[aj][b], jl);
 #pragma unroll
-            for (int c = 0; c < SEG; ++c) un[c] = v[c];
-          }
+          for (int a = 0; a < 4; ++a)
+            if (a >= aj) v[a][b] -= l[a] * u;
         }
-        cta_bar();
+        // the reciprocal of the next pivot, in the lane that owns it (hidden behind the barrier wait)
+        const int jn = j + 1;
+        if (tc == (jn & 15) && tr == (jn & 31)) {
+          const int an = min(jn >> 5, 3), bn = min(jn >> 4, 7);  // (aj, bj) or, at q == 15, the next block's
+          double d = v[aj][bj];
+          if (q == 15) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 8; ++b)
+                if (a == an && b == bn) d = v[a][b];
+          }
+          rinv_next = fast_rcp(d);
+        }
       }
-    } else {
-#pragma unroll 1
-      for (int i = 0; i <= SEG; ++i) cta_bar();
     }
   }
   if (bad) s_bad = 1;
-  cta_bar();
+  __syncthreads();
   if (tid == 0) *flag = s_bad;
 #pragma unroll
-  for (int c = 0; c < SEG; ++c) {
-    const int gc = q * SEG + c;
-    if (r < nb && gc < nb) S[(int64_t)gc * lds + r] = v[c];
-  }
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = tr + 32 * a, c = tc + 16 * b;
+      if (r < nb && c < nb) S[(int64_t)c * lds + r] = v[a][b];
+    }
 }
 
 // Inverses of the two triangular factors packed in S (nb x nb, ld lds): blockIdx.y = 0: X = L^-1
@@ -1268,17 +1267,11 @@ int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, in
     const int rc0 = mmr_func_smem(ctx, (const void*)lu_tri_inv_kernel, inv_smem);
     if (rc0) return rc0;
   }
-  static int seg = -1;
-  if (seg < 0) {
-    const char* e = getenv("MMR_LU_DIAG_SEG");
-    seg = e ? atoi(e) : 32;
-  }
   const int m = N - kb;
   double* Uinv = (double*)d_spec;
   int* d_flag = (int*)((char*)d_spec + sizeof(double) * NB * NB);
   const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, strm);
-  if (seg == 16) lu_diag_nopiv_kernel<16><<<1, 1024, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
-  else lu_diag_nopiv_kernel<32><<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
+  lu_diag_nopiv_tile_kernel<<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
   MMR_CHECK_LAUNCH(ctx);
   const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
   lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, strm>>>(S, m, nb, Linv, Uinv);
