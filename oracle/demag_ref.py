@@ -121,8 +121,12 @@ def match_pairs_indices(pos, quat, dim):
     return unique_inds, np.asarray(unique_inv_inds).reshape(-1)
 
 
-def demag_tensor_ref(pos, quat, dim, pairs_matching=False, split=1, max_dist=0):
+def demag_tensor_ref(pos, quat, dim, pairs_matching=False, split=1, max_dist=0, threads=1):
     """(3,n,n,3) array [k unit-pol][i source][j observer][l comp], A/m per tesla.
+
+    ``threads`` > 1 evaluates the ``split`` source chunks on a thread pool (numpy ufuncs release the
+    GIL): the same arithmetic, used by bench.py so that the CPU arm gets every host core -- the reference
+    itself runs this part on one thread.
 
     Restates demag.py:124-224 including the three passes (one per unit polarization,
     :182), ``split`` chunking of the source list (:202-218), the pairs_matching
@@ -166,14 +170,18 @@ def demag_tensor_ref(pos, quat, dim, pairs_matching=False, split=1, max_dist=0):
             else:
                 H_unit_pol = H_unique[unique_inv_inds]
         elif split > 1:
-            parts = []
-            for idx in np.array_split(np.arange(n), split):
-                if idx.size > 0:
-                    parts.append(
-                        getBH_cuboid_sources(
-                            "H", pos, pos[idx], quat[idx], dim[idx], pol_all[idx]
-                        )
-                    )
+            chunks = [idx for idx in np.array_split(np.arange(n), split) if idx.size > 0]
+
+            def one(idx, pol_all=pol_all):
+                return getBH_cuboid_sources("H", pos, pos[idx], quat[idx], dim[idx], pol_all[idx])
+
+            if threads > 1:
+                from concurrent.futures import ThreadPoolExecutor
+
+                with ThreadPoolExecutor(max_workers=threads) as pool:
+                    parts = list(pool.map(one, chunks))
+            else:
+                parts = [one(idx) for idx in chunks]
             H_unit_pol = np.concatenate(parts, axis=0)
         else:
             H_unit_pol = getBH_cuboid_sources("H", pos, pos, quat, dim, pol_all)
@@ -221,6 +229,7 @@ def apply_demag_ref(
     split=1,
     return_parts=False,
     timings=None,
+    threads=1,
 ):
     """Solved LOCAL-frame polarizations (n,3).  ``timings``: optional dict that receives the wall seconds of the
     three stages SURVEY 8d names (assembly, building Q with the dense S@T, LAPACK solve).
@@ -246,7 +255,7 @@ def apply_demag_ref(
 
     t0 = _time.perf_counter()
     T4 = demag_tensor_ref(
-        pos, quat, dim, pairs_matching=pairs_matching, split=split, max_dist=max_dist
+        pos, quat, dim, pairs_matching=pairs_matching, split=split, max_dist=max_dist, threads=threads
     )
     T = tensor_to_matrix(T4)
     t1 = _time.perf_counter()
