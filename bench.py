@@ -36,15 +36,24 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 # stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 behind Python's back
-# (NCCL prints its version banner there): point fd 1 at stderr for the whole process and keep a private
-# handle on the real stdout for the result line.
-_RESULT_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+# (NCCL prints its version banner there): main() points fd 1 at stderr for the whole process and keeps a
+# private handle on the real stdout for the result line.  (Not done at import: tests import make_workload.)
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line):
-    _RESULT_OUT.write(json.dumps(line) + "\n")
-    _RESULT_OUT.flush()
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 FLOP_PER_PAIR_ALIGNED = 2162.0  # SURVEY 8d convention (sqrt=20, log=50, atan2=65, add/mul=1)
 FLOP_PER_PAIR_ROTATED = 2288.0
@@ -488,6 +497,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiler runs only)")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
