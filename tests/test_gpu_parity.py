@@ -495,6 +495,50 @@ def test_config3_lattice_anisotropic_pairs_matching_reduced_vs_oracle():
     assert np.abs(got[:, 2] - got[perm][:, 2]).max() <= 1e-12 and np.abs(got[:, 0] + got[perm][:, 0]).max() <= 1e-12
 
 
+def test_config3_full_size_27000_cells_properties(ctx):
+    """BASELINE configs[2] at FULL size (27000 cells, Q = 52.5 GB, anisotropic chi, pairs_matching=True; the
+    CPU match_pairs would need 81.6 GB): size-independent properties -- the solution has the mirror symmetries
+    of the geometry and satisfies sampled rows of a DENSELY re-assembled system (independent of the dedupe
+    table and of GMRES)."""
+    from bench import make_workload
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~60 GB of device memory")
+    w = make_workload("lattice_27000")
+    n = len(w["pos"])
+    N = 3 * n
+    got, info = mmr.demag.apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"],
+                                             pairs_matching=True, solver="gmres", tol=1e-12, return_info=True)
+    assert info["gmres_relres"] <= 1e-12 and info["gmres_iters"] < 30
+    # mirror planes through the lattice centre: J_z even, J_x odd under x -> -x; J_z even, J_y odd under y -> -y
+    ctr = w["pos"].mean(axis=0)
+    key = np.round((w["pos"] - ctr) * 1e9).astype(np.int64)
+    order = np.lexsort(key.T[::-1])
+    for ax in (0, 1):
+        mir = key.copy()
+        mir[:, ax] *= -1
+        perm = np.empty(n, dtype=np.int64)
+        perm[order] = np.lexsort(mir.T[::-1])
+        gm = got[perm]
+        assert np.abs(got[:, 2] - gm[:, 2]).max() <= 1e-12 * np.abs(got).max()
+        assert np.abs(got[:, ax] + gm[:, ax]).max() <= 1e-12 * np.abs(got).max()
+    # sampled rows of a dense re-assembly
+    ld = (N + 15) // 16 * 16
+    d_pos, d_quat, d_dim = ctx.to_device(w["pos"]), ctx.to_device(w["quat"]), ctx.to_device(w["dim"])
+    d_chi = ctx.to_device(w["chi"].reshape(N))
+    xg = got.reshape(N)  # cells are axis-aligned: local = global frame
+    rhs = w["pol"].reshape(N)
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for c in rng.choice(n, size=24, replace=False):
+        row = ctx.empty(3, ld)
+        ctx.assemble(d_pos, d_quat, d_dim, row, ld, chi=d_chi, tgt_first=int(c), n_tgt_local=1)
+        r = row[:, :N].cpu().numpy() @ xg - rhs[3 * c:3 * c + 3]
+        worst = max(worst, float(np.abs(r).max()))
+    assert worst <= 1e-10 * np.abs(rhs).max(), worst
+
+
 def test_config5_magnet_array_max_dist_split_reduced_vs_oracle():
     """BASELINE configs[4] geometry at reduced size (3x3 magnets x 4^3 cells): max_dist truncation with the
     repaired semantics and split chunking, against the oracle."""
