@@ -319,6 +319,110 @@ def _rotate_rows(src_list, vecs, inverse=False):
     return rot.apply(vecs, inverse=inverse)
 
 
+def _is_block(g):
+    """A meshed Collection of the local object model standing for all its cells (objects.CellBlock)."""
+    return getattr(g, "_block", None) is not None
+
+
+def _group_len(g):
+    return len(g._block) if _is_block(g) else 1
+
+
+class _CellTable:
+    """The magnets of one ``apply_demag`` call as arrays.  Entries of ``groups`` are magnet objects (one
+    cell each, read attribute by attribute like the reference) or block collections (n cells each, read
+    and written as array slices)."""
+
+    def __init__(self, groups):
+        self.groups = groups
+        self.sizes = [_group_len(g) for g in groups]
+        self.n = int(sum(self.sizes))
+        self.offsets = np.concatenate([[0], np.cumsum(self.sizes)]).astype(int)
+        self.objects = [g for g in groups if not _is_block(g)]
+
+    def _fill(self, width, block_rows, object_row):
+        out = np.empty((self.n, width))
+        for g, o, m in zip(self.groups, self.offsets, self.sizes, strict=False):
+            if _is_block(g):
+                out[o:o + m] = block_rows(g._block)
+            else:
+                out[o] = object_row(g)
+        return out
+
+    def pol_local(self):
+        return self._fill(3, lambda b: b.pol,
+                          lambda s: (0.0, 0.0, 0.0) if s.polarization is None else s.polarization)
+
+    def rotate(self, vecs, inverse=False):
+        """Each cell's orientation (or its inverse) applied to the matching row (demag.py:420-428, :472-476)."""
+        out = np.empty((self.n, 3))
+        singles = [(o, g) for g, o in zip(self.groups, self.offsets, strict=False) if not _is_block(g)]
+        for g, o, m in zip(self.groups, self.offsets, self.sizes, strict=False):
+            if _is_block(g):
+                out[o:o + m] = g._block.rot.apply(vecs[o:o + m], inverse=inverse)
+        if singles:
+            idx = np.array([o for o, _ in singles])
+            out[idx] = _rotate_rows([g for _, g in singles], vecs[idx], inverse=inverse)
+        return out
+
+    def susceptibilities(self, susceptibility):
+        if susceptibility is not None:
+            return _convert_to_array(susceptibility, self.n, from_hierarchy=False)
+        if not any(_is_block(g) for g in self.groups):
+            return np.reshape(get_susceptibilities(self.groups), (self.n, 3), order="F")
+
+        def row(sus):  # one entry of the reference's per-source list (demag.py:71-88)
+            return _convert_to_array([sus, sus], 2, from_hierarchy=True)[0]
+
+        def of_block(blk_owner):
+            sus = blk_owner._block.attrs.get("susceptibility")
+            return row(_get_susceptibility_from_hierarchy(blk_owner) if sus is None else sus)
+
+        out = np.empty((self.n, 3))
+        for g, o, m in zip(self.groups, self.offsets, self.sizes, strict=False):
+            out[o:o + m] = of_block(g) if _is_block(g) else row(_get_susceptibility_from_hierarchy(g))
+        return out
+
+    def H_ext(self):
+        def of_block(owner):
+            h = owner._block.attrs.get("H_ext")
+            return get_H_ext(owner)[0] if h is None else h
+
+        out = np.empty((self.n, 3))
+        for g, o, m in zip(self.groups, self.offsets, self.sizes, strict=False):
+            h = of_block(g) if _is_block(g) else get_H_ext(g)[0]
+            if np.shape(h) != (3,):
+                msg = "Apply_demag input collection and H_ext must have same length."
+                raise ValueError(msg)
+            out[o:o + m] = h
+        return out
+
+    def require_cuboids(self, what):
+        _require_cuboids(self.objects, what)
+
+    def check_native(self):
+        _check_native_cells(self.objects)
+
+    def geometry(self):
+        """pos (n,3) [barycenter if present, demag.py:177], quat (n,4) scalar-last (:178), dim (n,3)."""
+        pos = self._fill(3, lambda b: b.pos, lambda s: getattr(s, "barycenter", s.position))
+        quat = self._fill(4, lambda b: b.rot.as_quat(), lambda s: s.orientation.as_quat())
+        dim = self._fill(3, lambda b: b.dim, lambda s: s.dimension)
+        return pos, quat, dim
+
+    def positions(self):
+        """The cells' ``position`` (demag.py:460; equals the barycenter for cuboids)."""
+        return self._fill(3, lambda b: b.pos, lambda s: s.position)
+
+    def write_polarizations(self, pol):
+        for g, o, m in zip(self.groups, self.offsets, self.sizes, strict=False):
+            if _is_block(g):
+                g._block.pol[:] = pol[o:o + m]
+                g._block.pol_set[:] = True
+            else:
+                g.polarization = pol[o]
+
+
 def _system_key(pos, quat, dim, chi, max_dist, solver):
     """Fingerprint of everything the system matrix depends on (bit-exact geometry, chi, max_dist)."""
     import hashlib
@@ -493,24 +597,31 @@ def apply_demag(
         collection = collection.copy()
     if style is not None:
         collection.style = style
-    srcs = collection.sources_all
-    src_with_paths = [src for src in srcs if np.ndim(src.position) != 1]
+    # Sources in ``sources_all`` order.  With the local object model a meshed collection appears as ONE
+    # group (its CellBlock, structure of arrays) instead of n cell objects; real magpylib collections and
+    # tiny systems take the per-object route of the reference (demag.py:380-381).
+    groups = collection._source_groups() if hasattr(collection, "_source_groups") else None
+    if groups is None or not any(_is_block(g) for g in groups) or sum(_group_len(g) for g in groups) <= 3:
+        groups = list(collection.sources_all)
+    src_with_paths = [g for g in groups if not _is_block(g) and np.ndim(g.position) != 1]
     if src_with_paths:
         msg = (
             f"{len(src_with_paths)} objects with paths, found. Demagnetization of "
             "objects with paths is not yet supported"
         )
         raise ValueError(msg)
-    magnets_list = [src for src in srcs if isinstance(src, BaseMagnet)]
-    currents_list = [src for src in srcs if isinstance(src, BaseCurrent)]
-    others_list = [src for src in srcs if not isinstance(src, BaseMagnet | BaseCurrent | Sensor)]
+    magnet_groups = [g for g in groups if _is_block(g) or isinstance(g, BaseMagnet)]
+    currents_list = [g for g in groups if not _is_block(g) and isinstance(g, BaseCurrent)]
+    others_list = [g for g in groups if not _is_block(g) and not isinstance(g, BaseMagnet | BaseCurrent | Sensor)]
     if others_list:
         counts_others = Counter(s.__class__.__name__ for s in others_list)
         counts_str = ", ".join(f"{count} {name}" for name, count in counts_others.items())
         msg = f"Only Magnet and Current sources supported. Incompatible objects found: {counts_str}"
         raise TypeError(msg)
-    n = len(magnets_list)
-    counts = Counter(s.__class__.__name__ for s in magnets_list)
+    n = sum(_group_len(g) for g in magnet_groups)
+    counts = Counter()
+    for g in magnet_groups:
+        counts["Cuboid" if _is_block(g) else g.__class__.__name__] += _group_len(g)
     inplace_str = " (inplace)" if inplace else ""
     lbl = collection.style.label
     coll_str = lbl or str(collection)
@@ -518,44 +629,35 @@ def apply_demag(
     demag_msg = f"Demagnetization{inplace_str} of {coll_str} with {n} cells ({counts_str})"
     info = {"n": n, "solver": solver}
     with timelog(demag_msg, min_log_time=min_log_time):
+        cells = _CellTable(magnet_groups)
         # J0 in the global frame (demag.py:420-428)
-        pol_local = np.array(
-            [(0.0, 0.0, 0.0) if src.polarization is None else src.polarization for src in magnets_list],
-            dtype=float,
-        ).reshape(n, 3)
-        pol_global = _rotate_rows(magnets_list, pol_local)
+        pol_global = cells.rotate(cells.pol_local())
 
-        # susceptibilities (demag.py:431), component-major -> (n,3)
-        sus = get_susceptibilities(magnets_list, susceptibility)
-        chi = np.reshape(sus, (n, 3), order="F")
+        # susceptibilities (demag.py:431), (n,3) = the reference's component-major vector reshaped
+        chi = cells.susceptibilities(susceptibility)
 
         # H_ext (demag.py:435-440)
-        H_ext = np.array(get_H_ext(*magnets_list), dtype=float)
-        if len(H_ext) != n:
-            msg = "Apply_demag input collection and H_ext must have same length."
-            raise ValueError(msg)
-        H_ext = H_ext.reshape(n, 3)
+        H_ext = cells.H_ext()
 
         if pairs_matching and split != 1:
             msg = "Pairs matching does not support splitting"
             raise ValueError(msg)
         if max_dist != 0:
-            _require_cuboids(magnets_list, "filter_distance")
+            cells.require_cuboids("filter_distance")
         elif pairs_matching:
-            _require_cuboids(magnets_list, "Pairs matching")
+            cells.require_cuboids("Pairs matching")
         if n == 0:
             return (collection if not inplace else None) if not return_info else (collection, info)
-        _check_native_cells(magnets_list)
+        cells.check_native()
 
-        pos, quat, dim = _cell_geometry(magnets_list)
+        pos, quat, dim = cells.geometry()
         if currents_list:
             # demag.py:456-463: pol_total += S . getB(currents, cell positions), fields from the CUDA
             # current-source kernel (mmr_field_currents)
             from .field import current_field
 
             with timelog("Add current sources contributions", min_log_time=min_log_time):
-                cell_pos = np.array([src.position for src in magnets_list], dtype=float).reshape(n, 3)
-                pol_global = pol_global + chi * current_field("B", currents_list, cell_pos, device=device)
+                pol_global = pol_global + chi * current_field("B", currents_list, cells.positions(), device=device)
         pol_new, solve_info = solve_cells_global(
             pos, quat, dim, pol_global, chi, H_ext, pairs_matching=pairs_matching, max_dist=max_dist,
             split=split, solver=solver, tol=tol, device=device, min_log_time=min_log_time,
@@ -564,9 +666,7 @@ def apply_demag(
         info.update(solve_info)
 
         # write back in each cell's local frame (demag.py:472-476); by magnet index (Appendix A Q7)
-        pol_write = _rotate_rows(magnets_list, pol_new, inverse=True)
-        for src, pol in zip(magnets_list, pol_write, strict=True):
-            src.polarization = pol
+        cells.write_polarizations(cells.rotate(pol_new, inverse=True))
 
     result = None if inplace else collection
     if return_info:

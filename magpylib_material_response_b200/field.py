@@ -13,25 +13,59 @@ from . import _native
 from ._compat import BaseCurrent, BaseMagnet, Circle, Collection, Cuboid, Polyline, Sensor
 
 
+def _is_block(g):
+    return getattr(g, "_block", None) is not None
+
+
 def _flatten_sources(sources):
+    """Leaf sources in order; a meshed collection of the local object model stays ONE entry (its
+    structure-of-arrays cell block is read as arrays, no per-cell objects)."""
     out = []
     for s in sources:
         if isinstance(s, Collection):
-            out.extend(s.sources_all)
+            out.extend(s._source_groups() if hasattr(s, "_source_groups") else s.sources_all)
         else:
             out.append(s)
     return out
 
 
+def _sensor_points(sensor):
+    """Global pixel positions of a sensor, (path length, *pixel shape, 3)."""
+    pix = np.asarray(sensor.pixel, dtype=float)
+    pos = np.asarray(sensor.position, dtype=float)
+    quat = np.asarray(sensor.orientation.as_quat(), dtype=float)
+    if pos.ndim == 1 and quat.ndim == 1:
+        return (sensor.orientation.apply(pix.reshape(-1, 3)) + pos).reshape(1, *pix.shape)
+    from scipy.spatial.transform import Rotation as R
+
+    p = max(len(np.atleast_2d(pos)), len(np.atleast_2d(quat)))
+    pos = np.broadcast_to(np.atleast_2d(pos), (p, 3)) if pos.ndim == 1 else pos
+    quat = np.broadcast_to(np.atleast_2d(quat), (p, 4)) if quat.ndim == 1 else quat
+    flat = pix.reshape(-1, 3)
+    pts = np.stack([R.from_quat(q).apply(flat) + t for q, t in zip(quat, pos, strict=True)])
+    return pts.reshape(p, *pix.shape)
+
+
 def _observer_array(observers):
-    """(points (m,3), output shape prefix)."""
+    """(points (m,3), output shape prefix).  Sensor observers follow magpylib's axis order
+    (path, sensor, *pixel shape) with length-1 path / sensor axes squeezed."""
     if isinstance(observers, Sensor):
-        pts = observers.global_pixels()
-        return pts, np.asarray(observers.pixel).shape[:-1]
+        pts = _sensor_points(observers)  # (p, *pix, 3)
+        shape = pts.shape[:-1] if pts.shape[0] > 1 else pts.shape[1:-1]
+        return pts.reshape(-1, 3), shape
     if isinstance(observers, list | tuple) and observers and all(isinstance(o, Sensor) for o in observers):
-        parts = [o.global_pixels() for o in observers]
-        shp = np.asarray(observers[0].pixel).shape[:-1]
-        return np.concatenate(parts, axis=0), (len(observers), *shp)
+        parts = [_sensor_points(o) for o in observers]
+        if len({a.shape[1:] for a in parts}) != 1:
+            msg = "all sensors must have the same pixel shape"
+            raise ValueError(msg)
+        p = max(a.shape[0] for a in parts)
+        parts = [np.broadcast_to(a[-1:], (p, *a.shape[1:])) if a.shape[0] == 1 else a for a in parts]
+        if len({a.shape[0] for a in parts}) != 1:
+            msg = "sensor paths must have the same length"
+            raise ValueError(msg)
+        pts = np.stack(parts, axis=1)  # (p, k, *pix, 3)
+        shape = pts.shape[:-1] if p > 1 else pts.shape[1:-1]
+        return pts.reshape(-1, 3), shape
     arr = np.asarray(observers, dtype=float)
     if arr.shape[-1] != 3:
         msg = f"observers must have shape (..., 3), got {arr.shape}"
@@ -41,12 +75,19 @@ def _observer_array(observers):
 
 def cell_arrays(cells):
     """SoA view of cuboid cells: pos (n,3), quat (n,4) scalar-last, dim (n,3), pol (n,3)."""
-    n = len(cells)
+    n = sum(len(c._block) if _is_block(c) else 1 for c in cells)
     pos = np.empty((n, 3))
     quat = np.empty((n, 4))
     dim = np.empty((n, 3))
     pol = np.zeros((n, 3))
-    for i, c in enumerate(cells):
+    i = 0
+    for c in cells:
+        if _is_block(c):  # a meshed collection: array slices
+            blk = c._block
+            m = len(blk)
+            pos[i:i + m], quat[i:i + m], dim[i:i + m], pol[i:i + m] = blk.pos, blk.rot.as_quat(), blk.dim, blk.pol
+            i += m
+            continue
         p = getattr(c, "barycenter", c.position)
         if np.ndim(p) != 1:
             msg = "objects with paths are not supported by the B200 field kernel"
@@ -56,6 +97,7 @@ def cell_arrays(cells):
         dim[i] = c.dimension
         if c.polarization is not None:
             pol[i] = c.polarization
+        i += 1
     return pos, quat, dim, pol
 
 
@@ -114,10 +156,14 @@ def getBH(field, sources, observers, sumup=True, squeeze=True, device=None):
     if field not in ("B", "H"):
         msg = "field must be 'B' or 'H'"
         raise ValueError(msg)
+    if not sumup or not squeeze:
+        # the kernel reduces over the sources on the device; per-source output is not produced
+        msg = "the B200 field path returns the summed, squeezed field only (sumup=True, squeeze=True)"
+        raise NotImplementedError(msg)
     srcs = _flatten_sources(sources)
-    cuboids = [s for s in srcs if isinstance(s, Cuboid)]
+    cuboids = [s for s in srcs if _is_block(s) or isinstance(s, Cuboid)]
     currents = [s for s in srcs if isinstance(s, BaseCurrent)]
-    bad = [s for s in srcs if not isinstance(s, Cuboid | BaseCurrent)]
+    bad = [s for s in srcs if not _is_block(s) and not isinstance(s, Cuboid | BaseCurrent)]
     if bad:
         kinds = sorted({type(s).__name__ for s in bad})
         if any(isinstance(s, BaseMagnet) for s in bad):

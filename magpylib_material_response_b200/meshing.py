@@ -14,7 +14,7 @@ from itertools import product
 
 import numpy as np
 
-from ._compat import BaseCurrent, Collection, Cuboid
+from ._compat import HAVE_MAGPYLIB, BaseCurrent, Collection, Cuboid
 from .utils import logger
 
 
@@ -67,12 +67,18 @@ def cells_from_dimension(dim, target_elems, min_val=1, strict_max=False, parity=
 
 
 def _collection_from_obj_and_cells(obj, cells, **style_kwargs):
-    """meshing.py:19-29: cells inherit susceptibility, collection takes the parent's pose."""
+    """meshing.py:19-29: cells inherit susceptibility, collection takes the parent's pose.  ``cells``
+    is a list of objects or a ``CellBlock`` (structure-of-arrays cells of the local object model)."""
     susceptibility = getattr(obj, "susceptibility", None)
-    if susceptibility is not None:
-        for cell in cells:
-            cell.susceptibility = susceptibility
-    coll = Collection(cells)
+    if isinstance(cells, list):
+        if susceptibility is not None:
+            for cell in cells:
+                cell.susceptibility = susceptibility
+        coll = Collection(cells)
+    else:
+        if susceptibility is not None:
+            cells.attrs["susceptibility"] = susceptibility
+        coll = Collection._from_block(cells)
     coll.style.update(obj.style.as_dict(), _match_properties=False)
     coll.style.update(coll._process_style_kwargs(**style_kwargs))
     coll.position = obj.position
@@ -109,14 +115,19 @@ def mesh_Cuboid(cuboid, target_elems, verbose=False, **kwargs):
         for d, n in zip(dim0, nnn, strict=True)
     ]
     grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
-    cells = [Cuboid(polarization=pol0, dimension=new_dim, position=pp) for pp in grid]
+    if HAVE_MAGPYLIB:  # pragma: no cover - real magpylib objects: one Cuboid per cell, as the reference
+        cells = [Cuboid(polarization=pol0, dimension=new_dim, position=pp) for pp in grid]
+    else:
+        from .objects import CellBlock
+
+        cells = CellBlock(grid, new_dim, pol=pol0)  # SoA cells; objects are views made on demand
     return _collection_from_obj_and_cells(cuboid, cells, **kwargs)
 
 
 def get_volume(obj, return_containing_cube_edge=False):
     """Volume of a Cuboid and, on request, the edge of the smallest origin-centred axis-aligned cube
     that contains it (meshing_utils.py:113-137; the B200 path has the Cuboid branch only)."""
-    if type(obj).__name__ != "Cuboid":
+    if not isinstance(obj, Cuboid):
         msg = "Unsupported object type for volume calculation"
         raise TypeError(msg)
     edges = np.asarray(obj.dimension, dtype=float)

@@ -356,6 +356,179 @@ class Cuboid(BaseMagnet):
         return float(np.prod(self._dimension))
 
 
+class CellBlock:
+    """Structure-of-arrays storage of the n Cuboid cells of one meshed collection: ``pos`` (n,3) centres,
+    ``dim`` (n,3) edge lengths, ``pol`` (n,3) local-frame polarizations with ``pol_set`` (n,) marking the
+    cells whose polarization is not None, ONE orientation ``rot`` shared by all cells (what
+    ``mesh_Cuboid`` produces: /root/reference/src/magpylib_material_response/meshing.py:60-95) and the
+    attributes every cell carries alike (``attrs``: susceptibility, H_ext; meshing.py:19-29).
+
+    The Python objects of the cells are ``CellView`` rows onto these arrays, created only when somebody
+    asks for them (``collection.children``, ``sources_all`` ...); ``apply_demag`` / ``getB`` read and write
+    the arrays directly, so the per-cell object cost of the reference (meshing.py:90-93, demag.py:380-381,
+    :420-428, :472-476) disappears from the hot path.
+    """
+
+    __slots__ = ("pos", "dim", "pol", "pol_set", "rot", "attrs", "custom")
+
+    def __init__(self, pos, dim, pol=None, rot=None, attrs=None):
+        self.pos = np.ascontiguousarray(pos, dtype=float).reshape(-1, 3).copy()
+        n = len(self.pos)
+        self.dim = np.ascontiguousarray(np.broadcast_to(np.asarray(dim, dtype=float), (n, 3))).copy()
+        self.pol = np.zeros((n, 3))
+        self.pol_set = np.zeros(n, dtype=bool)
+        if pol is not None:
+            self.pol[:] = np.asarray(pol, dtype=float)
+            self.pol_set[:] = True
+        self.rot = _IDENTITY if rot is None else _rot_single(rot)
+        self.attrs = dict(attrs or {})
+        self.custom = False  # a cell view received an attribute of its own: array fast paths are off
+
+    def __len__(self):
+        return len(self.pos)
+
+    def copy(self):
+        new = CellBlock.__new__(CellBlock)
+        new.pos, new.dim, new.pol, new.pol_set = self.pos.copy(), self.dim.copy(), self.pol.copy(), self.pol_set.copy()
+        new.rot = self.rot
+        new.attrs = _copy.deepcopy(self.attrs)
+        new.custom = False
+        return new
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
+    def shift(self, delta):
+        self.pos += delta
+
+    def rotate_about(self, rel, anchor):
+        self.pos[:] = anchor + rel.apply(self.pos - anchor)
+        self.rot = _rot_single(rel * self.rot)
+
+
+def _row_property(field):
+    def fget(self):
+        return getattr(self._blk, field)[self._i]
+
+    return fget
+
+
+class CellView(Cuboid):
+    """A Cuboid whose position / dimension / polarization are rows of its collection's ``CellBlock``
+    (reads return views, assignments write into the arrays).  Anything a block cannot represent -- a
+    path, an orientation of its own, leaving the collection -- first turns every cell of the block into
+    an ordinary ``Cuboid`` (``Collection._detach_block``)."""
+
+    _OWN = frozenset(("_blk", "_i", "_parent", "_style", "_id"))
+
+    def __init__(self, *args, **kwargs):
+        msg = "CellView objects are created by their Collection"
+        raise TypeError(msg)
+
+    @classmethod
+    def _make(cls, blk, i, parent):
+        new = cls.__new__(cls)
+        d = new.__dict__
+        d["_blk"], d["_i"], d["_parent"], d["_style"] = blk, i, parent, None
+        BaseGeo._ids += 1
+        d["_id"] = BaseGeo._ids
+        return new
+
+    def _detached(self):
+        """Detach the whole block; afterwards ``self`` is a plain Cuboid."""
+        self.__dict__["_parent"]._detach_block()
+
+    # pose --------------------------------------------------------------------------------------
+    @property
+    def _position(self):
+        return self._blk.pos[self._i]
+
+    @_position.setter
+    def _position(self, value):
+        value = np.asarray(value, dtype=float)
+        if value.shape == (3,):
+            self._blk.pos[self._i] = value
+        else:
+            self._detached()
+            self._position = value
+
+    @property
+    def _orientation(self):
+        return self._blk.rot
+
+    @_orientation.setter
+    def _orientation(self, value):
+        if value is self._blk.rot:
+            return
+        self._detached()
+        self._orientation = value
+
+    @property
+    def _dimension(self):
+        return self._blk.dim[self._i]
+
+    @_dimension.setter
+    def _dimension(self, value):
+        if value is None:
+            self._detached()
+            self._dimension = None
+        else:
+            self._blk.dim[self._i] = value
+
+    @property
+    def _polarization(self):
+        blk, i = self._blk, self._i
+        return blk.pol[i] if blk.pol_set[i] else None
+
+    @_polarization.setter
+    def _polarization(self, value):
+        blk, i = self._blk, self._i
+        if value is None:
+            blk.pol[i] = 0.0
+            blk.pol_set[i] = False
+        else:
+            blk.pol[i] = value
+            blk.pol_set[i] = True
+
+    @property
+    def style(self):
+        d = self.__dict__
+        if d["_style"] is None:
+            d["_style"] = Style()
+        return d["_style"]
+
+    @style.setter
+    def style(self, value):
+        self.__dict__["_style"] = value
+
+    # attributes shared by all cells of the block (susceptibility, H_ext) ----------------------------
+    def __getattr__(self, name):
+        attrs = self.__dict__["_blk"].attrs if "_blk" in self.__dict__ else {}
+        if name in attrs:
+            return attrs[name]
+        msg = f"{type(self).__name__!r} object has no attribute {name!r}"
+        raise AttributeError(msg)
+
+    def __setattr__(self, name, value):
+        if name not in CellView._OWN and not isinstance(getattr(type(self), name, None), property):
+            self.__dict__["_blk"].custom = True
+        object.__setattr__(self, name, value)
+
+    def __delattr__(self, name):
+        if name not in self.__dict__ and name in self._blk.attrs:
+            self._detached()
+        object.__delattr__(self, name)
+
+    def __deepcopy__(self, memo):
+        # a cell copied on its own becomes an ordinary Cuboid
+        new = Cuboid(position=self._position.copy(), orientation=self._orientation, dimension=self._dimension.copy(),
+                     polarization=None if self._polarization is None else self._polarization.copy())
+        new.style = self.style.copy()
+        for k, v in {**self._blk.attrs, **{k: v for k, v in self.__dict__.items() if k not in CellView._OWN}}.items():
+            setattr(new, k, _copy.deepcopy(v, memo))
+        return new
+
+
 class Sensor(BaseGeo):
     """Observer positions ``pixel`` in the sensor's local frame."""
 
@@ -370,14 +543,60 @@ class Sensor(BaseGeo):
 
 
 class Collection(BaseSource):
-    """Group of objects; moving/rotating the collection moves/rotates its children."""
+    """Group of objects; moving/rotating the collection moves/rotates its children.
+
+    A collection produced by ``mesh_Cuboid`` keeps its cells in a ``CellBlock`` (structure of arrays); the
+    ``CellView`` children are materialised on first access and every pose operation on the collection is
+    an array operation on the block.  Changing the child list of such a collection (``add`` / ``remove``)
+    converts it to ordinary ``Cuboid`` children first.
+    """
 
     def __init__(self, *children, position=(0.0, 0.0, 0.0), orientation=None, style=None, **kwargs):
         super().__init__(position, orientation, style, **kwargs)
-        self._children = []
+        self._block = None
+        self._kids = []
         self.add(*children)
 
+    @classmethod
+    def _from_block(cls, block):
+        new = cls()
+        new._block = block
+        new._kids = None
+        return new
+
     # -- tree ----------------------------------------------------------------------
+    @property
+    def _children(self):
+        if self._kids is None:
+            blk = self._block
+            self._kids = [CellView._make(blk, i, self) for i in range(len(blk))]
+        return self._kids
+
+    @_children.setter
+    def _children(self, value):
+        self._kids = value
+
+    def _detach_block(self):
+        """Turn the block's cells into ordinary Cuboids (keeps the identity of existing views)."""
+        blk = self._block
+        if blk is None:
+            return
+        kids = self._children
+        self._block = None
+        for c in kids:
+            d = c.__dict__
+            object.__setattr__(c, "__class__", Cuboid)
+            i = d.pop("_i")
+            d.pop("_blk")
+            style = d.pop("_style")
+            d["_position"] = blk.pos[i].copy()
+            d["_orientation"] = blk.rot
+            d["_dimension"] = blk.dim[i].copy()
+            d["_polarization"] = blk.pol[i].copy() if blk.pol_set[i] else None
+            d["style"] = style if style is not None else Style()
+            for k, v in blk.attrs.items():
+                d.setdefault(k, v)
+
     @property
     def children(self):
         return list(self._children)
@@ -386,7 +605,7 @@ class Collection(BaseSource):
         return iter(self._children)
 
     def __len__(self):
-        return len(self._children)
+        return len(self._block) if self._kids is None else len(self._kids)
 
     def __getitem__(self, i):
         return self._children[i]
@@ -398,6 +617,8 @@ class Collection(BaseSource):
                 flat.extend(c)
             else:
                 flat.append(c)
+        if flat:
+            self._detach_block()
         for c in flat:
             if not isinstance(c, BaseGeo):
                 msg = f"cannot add {type(c).__name__!r} to a Collection"
@@ -408,12 +629,14 @@ class Collection(BaseSource):
             if c._parent is self:
                 continue  # already a child
             if c._parent is not None:
-                c._parent._children = [x for x in c._parent._children if x is not c]
+                c._parent.remove(c)
             c._parent = self
             self._children.append(c)
         return self
 
     def remove(self, *children):
+        if children:
+            self._detach_block()
         for c in children:
             self._children = [x for x in self._children if x is not c]
             c._parent = None
@@ -424,6 +647,20 @@ class Collection(BaseSource):
             yield c
             if isinstance(c, Collection):
                 yield from c._walk()
+
+    def _source_groups(self):
+        """The sources below this collection in ``sources_all`` order, with every un-customised cell
+        block as ONE entry (the owning Collection) instead of its n cells."""
+        out = []
+        if self._block is not None and not self._block.custom:
+            out.append(self)
+            return out
+        for c in self._children:
+            if isinstance(c, Collection):
+                out.extend(c._source_groups())
+            elif isinstance(c, BaseMagnet | BaseCurrent):
+                out.append(c)
+        return out
 
     @property
     def children_all(self):
@@ -446,44 +683,57 @@ class Collection(BaseSource):
         old = self._position
         if value.ndim == 1 and old.ndim == 1:
             delta = value - old
-            for c in self._walk_direct():
-                c._shift(delta)
+            if self._block is not None:
+                self._block.shift(delta)
+            else:
+                for c in self._children:
+                    c._shift(delta)
         else:
+            self._detach_block()
             newp = np.atleast_2d(value)
             oldp = np.atleast_2d(old)
             p = max(len(newp), len(oldp))
             oldp = np.vstack([oldp, np.repeat(oldp[-1:], p - len(oldp), axis=0)])
             newp = np.vstack([newp, np.repeat(newp[-1:], p - len(newp), axis=0)])
-            for c in self._walk_direct():
+            for c in self._children:
                 c._shift(newp - oldp)
         self._position = value
 
     def _set_orientation(self, value):
-        old = self._orientation
-        rel = value * old.inv()
-        anchor = self._position
-        kids = self._children
-        single = np.asarray(rel.as_quat()).ndim == 1 and anchor.ndim == 1
-        if (
-            single
-            and len(kids) > 8
-            and all(not isinstance(c, Collection) and c._position.ndim == 1 for c in kids)
-            and all(c._orientation is kids[0]._orientation for c in kids)
-        ):
-            # fast path for meshes: leaf children sharing one orientation object
-            P = np.array([c._position for c in kids])
-            P = anchor + rel.apply(P - anchor)
-            new_o = _rot_single(rel * kids[0]._orientation)
-            for c, p in zip(kids, P, strict=True):
-                c._position = p
-                c._orientation = new_o
-        else:
-            for c in kids:
-                c._rotate_about(rel, anchor)
+        rel = value * self._orientation.inv()
+        self._rotate_children(rel, self._position)
         self._orientation = value
 
-    def _walk_direct(self):
-        return list(self._children)
+    def _rotate_children(self, rel, anchor):
+        anchor = np.asarray(anchor, dtype=float)
+        single = np.asarray(rel.as_quat()).ndim == 1 and anchor.ndim == 1
+        if self._block is not None:
+            if single:
+                self._block.rotate_about(rel, anchor)
+                return
+            self._detach_block()
+        for c in self._children:
+            c._rotate_about(rel, anchor)
+
+    def rotate(self, rotation, anchor=None, start="auto"):
+        """Rotate the collection AND its children about ``anchor`` (default: the collection's own
+        position), as magpylib's Collection does."""
+        rot = _as_rotation(rotation)
+        anc = self._position if anchor is None else np.array(anchor, dtype=float) * np.ones(3)
+        self._rotate_about(rot, anc)
+        return self
+
+    def __deepcopy__(self, memo):
+        if self._block is not None and self._block.custom:
+            self._detach_block()
+        if self._block is None:
+            return super().__deepcopy__(memo)
+        kids, self._kids = self._kids, None  # the views are not copied: the new block makes its own
+        try:
+            new = super().__deepcopy__(memo)
+        finally:
+            self._kids = kids
+        return new
 
     def _process_style_kwargs(self, **kwargs):
         out = {}
@@ -502,19 +752,22 @@ class Collection(BaseSource):
 def _shift(self, delta):
     """Translate an object (and, for collections, its children) by delta ((3,) or (p,3))."""
     delta = np.asarray(delta, dtype=float)
+    if isinstance(self, Collection):
+        if self._block is not None and delta.ndim == 1 and self._position.ndim == 1:
+            self._block.shift(delta)
+        else:
+            self._detach_block()
+            for c in self._children:
+                c._shift(delta)
     if delta.ndim == 2 and self._position.ndim == 1:
         self._pad_orientation(len(delta))
-    if isinstance(self, Collection):
-        for c in self._children:
-            c._shift(delta)
     self._position = self._position + delta
 
 
 def _rotate_about(self, rel, anchor):
     """Rotate an object (and children) by ``rel`` about ``anchor`` ((3,) or (p,3))."""
     if isinstance(self, Collection):
-        for c in self._children:
-            c._rotate_about(rel, anchor)
+        self._rotate_children(rel, anchor)
     anchor = np.asarray(anchor, dtype=float)
     relq = np.asarray(rel.as_quat())
     if relq.ndim == 1 and self._position.ndim == 1 and anchor.ndim == 1:

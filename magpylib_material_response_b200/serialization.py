@@ -68,6 +68,8 @@ def _plain(value, scalar):
 def _serialize_recursive(obj, parent="warn"):
     """Object -> JSON-compatible dict with a namespaced ``type`` tag (utils.py:110-173)."""
     tag = _TAG_OF.get(type(obj))
+    if tag is None and type(obj).__name__ == "CellView":  # a row of a meshed collection's cell block
+        tag = "magnet.Cuboid"
     if tag is None:
         msg = (
             f"Unsupported object type: {obj.__class__.__name__!r}. "
