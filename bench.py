@@ -9,14 +9,22 @@ entries) and solve Q x = J0 + chi*H_ext.  Headline unit: T-entries per second of
 (9 n^2 / step seconds); ms_per_step is the apply_demag device time itself.
 
   value  : inputs (cell geometry, chi, rhs) already resident in HBM, CUDA events around K steps.
-  e2e    : the same step through the public array-level API `apply_demag_arrays` with HOST numpy
-           buffers -- H2D of the geometry and D2H of the solution inside the timed region.
-  roofline     : dominant kernel (LU trailing DMMA update, or the matvec for --solver gmres),
-                 timed live with CUDA events inside the library (mmr_ctx_profile).
+  e2e    : the same step through the reference-signature object API -- apply_demag(Collection) on
+           mesh_Cuboid objects (host objects in, solved host objects out; copy(), H2D of the geometry and
+           D2H of the solution inside the timed region), K steps, wall clock between synchronizes.
+  e2e_arrays   : the same through the array-level API apply_demag_arrays (host numpy in/out).
+  parity_check : before timing, a 1728-cell two-magnet system solved with LU and GMRES through the public
+                 API on ALL ranks and compared with the CPU oracle on rank 0 (non-zero exit above 1e-8).
+  config4      : (N >= 2) after the timed region, one step of BASELINE configs[3] (64 000 cells, 295 GB).
+  roofline     : dominant kernel (LU trailing DMMA update, or the matvec for --solver gmres), timed live
+                 with CUDA events inside the library (mmr_ctx_profile); FP64 peaks measured in this run
+                 (mmr_fp64_peaks) right before the timed region.
   cpu_baseline : the numpy oracle (restated reference path) on a bounded sample, rank 0, N=1.
 
---impl reference times the reference's own CPU algorithm (oracle port: magpylib is not
-installable here) on the host cores for the same metric.
+--impl reference times the reference's own CPU algorithm (oracle port: magpylib is not installable here,
+see DESIGN.md) on the host cores for the same metric and config: ONE full-size step is always taken
+(recorded in cpu_baseline.full_size with its stage times); the W + K steps run at full size when that fits
+the time budget (MMR_REF_BUDGET_S, default 540 s), otherwise on the largest sample of the workload that does.
 """
 
 from __future__ import annotations
@@ -31,7 +39,15 @@ import sys
 import tempfile
 import time
 
-import numpy as np
+# Host threads for the CPU arm: torchrun exports OMP_NUM_THREADS=1 to its workers, which would run the
+# oracle's BLAS / LAPACK on one core.  Rank 0 -- the only rank that ever runs the oracle --
+# claims every core; this has to happen before numpy loads its BLAS.
+CPU_THREADS = os.cpu_count() or 1
+if int(os.environ.get("RANK", "0")) == 0:
+    for _var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_var] = str(CPU_THREADS)
+
+import numpy as np  # noqa: E402
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -177,6 +193,52 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
+# shared description of a workload: BOTH arms print this dict as `config`
+# ----------------------------------------------------------------------------------------
+def bench_config(name, w, solver):
+    n = len(w["pos"])
+    N = 3 * n
+    q_gb = 8.0 * N * N / 1e9
+    return {"workload": name, "desc": w["desc"], "n_cells": n, "matrix_order": N,
+            "solver": "lu (dgesv-equivalent: LU with partial pivoting, 1 rhs)" if solver == "lu" else solver,
+            "l2": "inputs larger than L2 (Q is %.1f GB)" % q_gb if q_gb > 0.5 else "256 MB flush buffer written before every step"}
+
+
+def make_collection(name):
+    """The workload as the objects a user of the reference API holds: Cuboids meshed with mesh_Cuboid
+    (docs/examples/soft_magnets.md:47-57 for two_magnets_*), susceptibilities / H_ext as attributes."""
+    from magpylib_material_response_b200 import Collection, Cuboid, mesh_Cuboid
+
+    n = int(name.split("_")[-1])
+    if name.startswith("two_magnets_"):
+        a = round(n ** (1 / 3))
+        nnn = (a, a, a // 2)
+        hard = Cuboid(polarization=(0, 0, 1), dimension=(1e-3, 1e-3, 2e-3)).move((0, 0, 0.5e-3))
+        hard.susceptibility = 0.5
+        soft = Cuboid(polarization=(0, 0, 0), dimension=(1e-3, 1e-3, 1e-3))
+        soft.rotate_from_angax(45, "y").move((1.5e-3, 0, 0))
+        soft.susceptibility = 1000.0
+        return Collection(mesh_Cuboid(hard, nnn), mesh_Cuboid(soft, nnn))
+    if name.startswith("soft_cube_"):
+        a = round(n ** (1 / 3))
+        cube = Cuboid(polarization=(0, 0, 0), dimension=(1e-3, 1e-3, 1e-3))
+        cube.susceptibility = 1000.0
+        coll = mesh_Cuboid(cube, (a, a, a))
+        coll.H_ext = (0.0, 0.0, 1.0)
+        return coll
+    return None
+
+
+def collection_polarizations(coll):
+    """Local-frame polarizations of all cells, (n,3), without creating cell objects."""
+    parts = []
+    for g in coll._source_groups():
+        blk = getattr(g, "_block", None)
+        parts.append(blk.pol if blk is not None else np.asarray(g.polarization, dtype=float)[None, :])
+    return np.vstack(parts)
+
+
+# ----------------------------------------------------------------------------------------
 # reference arm / cpu baseline (oracle port on host cores)
 # ----------------------------------------------------------------------------------------
 def cpu_sample_workload(name, n_sample):
@@ -184,43 +246,63 @@ def cpu_sample_workload(name, n_sample):
     return make_workload(f"{kind}_{n_sample}")
 
 
-CPU_THREADS = os.cpu_count() or 1
-
-
 def time_oracle_step(w, split=None, stages=None):
     """One full reference step on the CPU: 3 getH passes, dense S@T, np.linalg.solve.  The getH passes run
     on a thread pool over source chunks (bit-identical to the single-threaded order; the reference itself
     runs them on one thread), BLAS/LAPACK on all cores: every host thread the path can use."""
+    from threadpoolctl import threadpool_limits
+
     from oracle import demag_ref as oref
 
-    split = max(4, 2 * CPU_THREADS) if split is None else split
+    n = len(w["pos"])
+    if split is None:  # keep the ~60 live n_src x n temporaries of a getH chunk below ~1 GB per thread
+        split = max(4, 2 * CPU_THREADS, int(np.ceil(n * n * 60 * 8 * CPU_THREADS / 16e9)))
     t0 = time.perf_counter()
-    oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], H_ext=w["H_ext"], split=split, timings=stages,
-                         threads=CPU_THREADS)
+    with threadpool_limits(limits=CPU_THREADS):
+        oref.apply_demag_ref(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], H_ext=w["H_ext"], split=split,
+                             timings=stages, threads=CPU_THREADS)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(name, budget_s=20.0):
-    """Oracle timed on a bounded sample of the same workload geometry."""
-    n_sample = 2000 if "two_magnets" in name else 1728
+def host_mem_available():
+    try:
+        import psutil
+
+        return float(psutil.virtual_memory().available)
+    except Exception:  # pragma: no cover
+        return 0.0
+
+
+def oracle_fits(n):
+    """The reference path keeps ~7 dense N x N FP64 arrays alive (T4, T, S, S@T, eye, Q, LAPACK copy)."""
+    return 7.5 * 8.0 * (3 * n) ** 2 < 0.8 * host_mem_available()
+
+
+def sample_sizes(name):
+    """Cell counts of the workload family, largest first (cube edges in steps of 2)."""
+    n_full = int(name.split("_")[-1])
+    a_full = round(n_full ** (1 / 3))
+    return [a ** 3 for a in range(a_full, 5, -2)]
+
+
+def cpu_baseline(name, budget_s=30.0):
+    """Oracle timed on a bounded sample of the same workload geometry (about 10-30 s of CPU work)."""
+    if name.startswith(("two_magnets_", "soft_cube_")):
+        n_sample = next((m for m in sample_sizes(name) if m <= 4096), 1000)
+    else:
+        n_sample = 1728
     w = cpu_sample_workload(name, n_sample)
     n = len(w["pos"])
     stages = {}
     t = time_oracle_step(w, stages=stages)
-    reps = 1
-    while t * (reps + 1) < budget_s / 2 and reps < 3:
-        st = {}
-        t2 = time_oracle_step(w, stages=st)
-        if t2 < t:
-            t, stages = t2, st
-        reps += 1
     return {
         "value": 9.0 * n * n / t, "unit": "T-entries/s", "cores": CPU_THREADS, "kind": "port",
         "stages_s": {k: round(v, 4) for k, v in stages.items()},
         "assembly_entries_per_s": 9.0 * n * n / stages["assembly_s"],
-        "sample": f"{w['desc']} (reduced from the full workload), full reference step "
+        "sample": f"{w['desc']} (reduced from the full workload), one full reference step "
                   f"(3 getH passes + dense S@T + LAPACK dgesv) in {t:.2f} s; getH passes on a {CPU_THREADS}-thread pool over "
-                  "source chunks (the reference runs them on one thread), BLAS/LAPACK on all cores",
+                  "source chunks (the reference runs them on one thread), BLAS/LAPACK on all cores; the full-size step is "
+                  "timed by `bench.py --impl reference` (cpu_baseline.full_size)",
         "seconds": t, "n_cells": n,
     }
 
@@ -230,28 +312,72 @@ def run_reference(args):
     if rank != 0:
         return
     name = args.workload or default_workload(args.gpus)
+    w_full = make_workload(name)
+    n_full = len(w_full["pos"])
+    budget = float(os.environ.get("MMR_REF_BUDGET_S", "540"))
     total = args.steps + args.warmup
-    n_sample = 2000 if total <= 6 else 1000
-    if "soft_cube" in name:
-        n_sample = 1728 if total <= 6 else 1000
-    w = cpu_sample_workload(name, n_sample)
+    t_begin = time.perf_counter()
+
+    # (1) one full-size step, always (when the host can hold it)
+    full = None
+    if oracle_fits(n_full):
+        st = {}
+        t_full = time_oracle_step(w_full, stages=st)
+        full = {"n_cells": n_full, "seconds": round(t_full, 3), "stages_s": {k: round(v, 3) for k, v in st.items()},
+                "value": 9.0 * n_full * n_full / t_full, "unit": "T-entries/s"}
+    # (2) size of the W + K steps: full size if the budget allows, else the largest sample that fits.
+    # Model from the full-size stage times: assembly ~ n^2, dense S@T and dgesv ~ n^3.
+    used = time.perf_counter() - t_begin
+    steps_left = total - (1 if full else 0)
+    if full:
+        asm, cub = full["stages_s"]["assembly_s"], full["stages_s"]["build_Q_s"] + full["stages_s"]["solve_s"]
+        nf = n_full
+    else:  # calibrate on a small sample
+        wc = cpu_sample_workload(name, 1000)
+        st = {}
+        time_oracle_step(wc, stages=st)
+        asm, cub, nf = st["assembly_s"], st["build_Q_s"] + st["solve_s"], len(wc["pos"])
+        used = time.perf_counter() - t_begin
+
+    def predict(m):
+        return 1.15 * (asm * (m / nf) ** 2 + cub * (m / nf) ** 3)
+
+    n_run = None
+    for m in sample_sizes(name):
+        if (m == n_full and not full) or not oracle_fits(m):
+            continue
+        if steps_left * predict(m) <= budget - used:
+            n_run = m
+            break
+    if n_run is None:
+        n_run = sample_sizes(name)[-1]
+    w = w_full if n_run == n_full else cpu_sample_workload(name, n_run)
     n = len(w["pos"])
-    for _ in range(args.warmup):
+    times = []
+    done_warm = 1 if (full and n_run == n_full) else 0  # the full-size step above is the first warm-up
+    for _ in range(max(0, args.warmup - done_warm)):
         time_oracle_step(w)
     times = [time_oracle_step(w) for _ in range(args.steps)]
     t = sum(times) / len(times)
     value = 9.0 * n * n / t
+    if n_run == n_full:
+        sample = f"full size: {w['desc']}; every step is the whole workload, {t:.2f} s per step"
+    else:
+        sample = (f"{w['desc']} -- the largest member of the workload family whose {total} steps fit the {budget:.0f} s "
+                  f"budget ({t:.2f} s per step); the full-size step ({n_full} cells) is in full_size")
+    sample += (f"; one step = the reference's 3 getH passes + dense S@T + LAPACK dgesv; getH passes on a {CPU_THREADS}-thread "
+               "pool over source chunks (the reference runs them on one thread), BLAS/LAPACK on all cores")
     line = {
         "impl": "reference", "metric": "apply_demag_T_entries_per_s", "value": value, "unit": "T-entries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "sample": w["desc"], "solver": "numpy.linalg.solve (dgesv)",
-                   "note": "restated oracle of the reference CPU path (magpylib not installable); bounded sample of the workload"},
+        "config": bench_config(name, w_full, "lu"),
         "cpu_baseline": {"value": value, "unit": "T-entries/s", "cores": CPU_THREADS, "kind": "port",
-                         "sample": f"{w['desc']}; {t:.2f} s per full reference step (getH passes on a {CPU_THREADS}-thread pool, "
-                                   "BLAS/LAPACK on all cores)"},
+                         "sample": sample, "sample_n_cells": n, "full_size": full,
+                         "note": "restated oracle of the reference CPU path (magpylib is not installable here, DESIGN.md 2)"},
         "e2e": {"value": value, "unit": "T-entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "host_threads_env": {v: os.environ.get(v) for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS")},
     }
     emit(line)
 
@@ -263,18 +389,118 @@ def default_workload(ngpus):
     return "two_magnets_8000"
 
 
-def load_peaks():
-    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "fp64_dmma_tflops": 37.1,
-             "fp64_fma_tflops": 33.9, "fp64_src": "profiles/fp64_peaks_r1.json (tools/fp64_peaks.cu, measured on this pool)"}
+def load_peaks(ctx):
+    """Roofline denominators: HBM from MEASURED_PEAKS.json (driver-written), FP64 measured NOW on this
+    device through the C ABI (mmr_fp64_peaks); the tracked round-1 file is only the cross-check."""
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)"}
     mp = ROOT / "MEASURED_PEAKS.json"
     if mp.exists():
         d = json.loads(mp.read_text())
         peaks["hbm_gbs"], peaks["hbm_src"] = d.get("hbm_gbs", peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    fma, dmma = ctx.fp64_peaks()
+    peaks["fp64_fma_tflops"], peaks["fp64_dmma_tflops"] = fma, dmma
+    peaks["fp64_src"] = ("mmr_fp64_peaks, measured in this run right before the timed region "
+                         f"(DMMA {dmma:.2f} TF, FMA {fma:.2f} TF; burst figure of independent instruction chains on all SMs)")
     fp = ROOT / "profiles" / "fp64_peaks_r1.json"
     if fp.exists():
         d = json.loads(fp.read_text())
-        peaks["fp64_dmma_tflops"], peaks["fp64_fma_tflops"] = d["fp64_dmma_tflops"], d["fp64_fma_tflops"]
+        peaks["fp64_src"] += f"; round-1 file: DMMA {d['fp64_dmma_tflops']:.2f}, FMA {d['fp64_fma_tflops']:.2f}"
     return peaks
+
+
+PARITY_TOL = 1e-8  # north star: solved polarizations within rtol 1e-8
+
+
+def parity_check(world, rank):
+    """Driver-visible correctness of THIS run's configuration (N ranks): a 1728-cell two-magnet system
+    (rotated chi = 1000 cube included) through the public array API on all ranks -- LU, GMRES, and the
+    pairs_matching / split / demag_store variants -- against the CPU oracle on rank 0."""
+    from magpylib_material_response_b200.demag import apply_demag_arrays
+
+    w = make_workload("two_magnets_1728")
+    n = len(w["pos"])
+    geo = (w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"])
+    runs = [("lu", {}), ("gmres", {}), ("lu", {"split": 8}), ("lu", {"pairs_matching": True})]
+    xs = []
+    for solver, kw in runs:
+        xs.append(apply_demag_arrays(*geo, solver=solver, tol=1e-12, **kw))
+    store = {}
+    apply_demag_arrays(*geo, solver="lu", demag_store=store)
+    xs.append(apply_demag_arrays(*geo, solver="lu", demag_store=store))  # second call: factors reused
+    runs.append(("lu", {"demag_store": "hit"}))
+    out = []
+    if rank == 0:
+        from threadpoolctl import threadpool_limits
+
+        from oracle import demag_ref as oref
+
+        with threadpool_limits(limits=CPU_THREADS):
+            ref = oref.apply_demag_ref(*geo[:5], H_ext=w["H_ext"], split=2 * CPU_THREADS, threads=CPU_THREADS)
+        scale = np.abs(ref).max()
+        for (solver, kw), x in zip(runs, xs, strict=True):
+            out.append({"solver": solver, **kw, "n": n, "max_rel_err": float(np.abs(x - ref).max() / scale)})
+    return out
+
+
+def run_config4(ctx, world, rank, dist):
+    """One step of BASELINE configs[3] (64 000-cell soft-iron cube, N = 192 000, 295 GB of Q) on the N
+    ranks of this run: distributed assembly + LU + solve, then the true residual on a fresh Q."""
+    import torch
+
+    from magpylib_material_response_b200.demag import _padded_ld
+    from magpylib_material_response_b200.distributed import DEFAULT_TGT_BLOCK, owned_cells
+
+    w = make_workload("soft_cube_64000")
+    n = len(w["pos"])
+    N = 3 * n
+    ld = _padded_ld(N)
+    tgt_block = DEFAULT_TGT_BLOCK
+    n_local = len(owned_cells(n, tgt_block, world, rank))
+    need = 8.0 * 3 * n_local * ld + 8.0 * N * (2 * 256 + 128 + 16) + 2e9
+    torch.cuda.empty_cache()
+    free = torch.cuda.mem_get_info(ctx.device)[0]
+    ok = torch.tensor([1 if need < free else 0], device=ctx.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        return {"skipped": f"needs {need / 1e9:.0f} GB per GPU at {world} GPUs, {free / 1e9:.0f} GB free"}
+    rhs = (w["pol"] + w["chi"] * w["H_ext"]).reshape(N)  # identity orientation
+    d_pos, d_quat, d_dim = ctx.to_device(w["pos"]), ctx.to_device(w["quat"]), ctx.to_device(w["dim"])
+    d_chi, d_rhs = ctx.to_device(w["chi"].reshape(N)), ctx.to_device(rhs)
+    Q = ctx.empty(3 * n_local, ld)
+    d_x = ctx.empty(N)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def assemble():
+        ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, n_tgt_local=n_local, tgt_block=tgt_block,
+                     tgt_nparts=world, tgt_part=rank)
+
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.set_profiling(True)
+    ev[0].record()
+    assemble()
+    ev[1].record()
+    d_x.copy_(d_rhs)
+    info = ctx.lu_solve_dist(N, 3 * n_local, tgt_block, Q, ld, d_x)
+    ev[2].record()
+    torch.cuda.synchronize()
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    tt = torch.tensor([ev[0].elapsed_time(ev[2]), ev[0].elapsed_time(ev[1]), prof["gemm"][0]], dtype=torch.float64,
+                      device=ctx.device)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_all, t_asm, t_gemm = (float(v) * 1e-3 for v in tt)
+    assemble()
+    _, relres = ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_rhs, d_x, tol=1.0, restart=1, maxit=1)
+    x = d_x.cpu().numpy().reshape(n, 3)
+    del Q
+    torch.cuda.empty_cache()
+    lu_s = t_all - t_asm
+    return {"workload": "soft_cube_64000", "n_cells": n, "matrix_order": N, "q_gb_total": 8.0 * N * N / 1e9,
+            "apply_demag_s": t_all, "assembly_s": t_asm, "assembly_entries_per_s": 9.0 * n * n / t_asm,
+            "lu_factor_tflops": (2.0 / 3.0) * N ** 3 / lu_s / 1e12, "gemm_frac": t_gemm / t_all,
+            "relres": relres, "lu_info": int(info), "mean_Jz": float(x[:, 2].mean()),
+            "note": "one un-warmed step (max over ranks, CUDA events); relres = ||b - Qx||/||b|| on a re-assembled Q"}
 
 
 def run_ours(args):
@@ -282,7 +508,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from magpylib_material_response_b200 import _native
-    from magpylib_material_response_b200.demag import _padded_ld, apply_demag_arrays
+    from magpylib_material_response_b200.demag import _padded_ld, apply_demag, apply_demag_arrays
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -300,7 +526,26 @@ def run_ours(args):
     ctx = _native.default_context(local_rank)
     if world > 1:
         ctx.comm_init_from_torch()
-    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness of this configuration first (not timed) --------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(world, rank)
+        bad = torch.tensor([1 if any(not (r["max_rel_err"] <= PARITY_TOL) for r in parity) else 0], device=ctx.device)
+        if world > 1:
+            dist.broadcast(bad, src=0)
+        if int(bad.item()):
+            if rank == 0:
+                emit({"metric": "apply_demag_T_entries_per_s", "value": None, "n_gpus": world, "parity_check": parity,
+                      "error": f"parity check failed (tolerance {PARITY_TOL})"})
+            if world > 1:
+                dist.destroy_process_group()
+            raise SystemExit(3)
 
     from scipy.spatial.transform import Rotation as R
 
@@ -321,7 +566,7 @@ def run_ours(args):
     ipiv = ctx.empty(N, dtype=torch.int32)
     d_x = ctx.empty(N)
     solver = args.solver
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device) if 8.0 * N * ld * 3 < 512e6 else None
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device) if 8.0 * N * N < 0.5e9 else None
 
     def step():
         if flush is not None:
@@ -344,13 +589,10 @@ def run_ours(args):
         d_x.zero_()
         return ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_rhs, d_x, tol=args.tol, restart=args.restart, maxit=5000)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(args.warmup):
         step()
+    barrier()
+    peaks = load_peaks(ctx)  # FP64 peaks measured now, clocks already up from the warm-up steps
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.set_profiling(True)
@@ -372,6 +614,7 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev = float(tt.item())
     t_step = t_dev / args.steps
+    x_dev = d_x.cpu().numpy().reshape(n, 3)
 
     # residual of the last solution (not timed): ||Q x - b|| / ||b|| on a fresh Q
     ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, n_tgt_local=n_local, tgt_block=tgt_block,
@@ -384,32 +627,57 @@ def run_ours(args):
     else:
         # distributed true residual ||b - Q x|| / ||b|| (tol=1: report the residual of x, no iterations)
         _, relres = ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_rhs, d_x, tol=1.0, restart=1, maxit=1)
+    del Q
+    torch.cuda.empty_cache()
 
-    # e2e through the public array API with host buffers: every rank passes the same host arrays and gets
-    # the full solution back (H2D of geometry/chi/rhs and D2H of the solution inside the timed region);
-    # wall clock between barriers, max over ranks
-    e2e = None
-    if not args.no_e2e:
-        del Q
-        torch.cuda.empty_cache()
-        kw = dict(solver=solver, tol=args.tol)
-        apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw)
+    # ---- end to end through the public APIs with HOST inputs/outputs -------------------------------
+    # every rank makes the same call (SPMD) and gets the full solution back; wall clock between
+    # synchronizes, max over ranks, K steps
+    def time_calls(fn):
+        fn()  # warm (allocations)
         barrier()
-        reps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
-        for _ in range(reps):
-            xs = apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw)
+        for _ in range(args.steps):
+            res = fn()
         torch.cuda.synchronize()
-        t_e2e = (time.perf_counter() - t0) / reps
+        t = (time.perf_counter() - t0) / args.steps
         if world > 1:
-            tt = torch.tensor([t_e2e], dtype=torch.float64, device=ctx.device)
+            tt = torch.tensor([t], dtype=torch.float64, device=ctx.device)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_e2e = float(tt.item())
-        h2d = 8 * (n * 3 + n * 4 + n * 3 + N + N) * world  # pos, quat, dim, chi, rhs on every rank
-        d2h = 8 * N * world
-        e2e = {"value": 9.0 * n * n / t_e2e, "unit": "T-entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "seconds_per_step": t_e2e, "api": "magpylib_material_response_b200.demag.apply_demag_arrays (host numpy in/out)"}
-        del xs
+            t = float(tt.item())
+        return t, res
+
+    e2e = e2e_arrays = None
+    h2d = 8 * (n * 3 + n * 4 + n * 3 + N + N) * world  # pos, quat, dim, chi, rhs on every rank
+    d2h = 8 * N * world
+    if not args.no_e2e:
+        kw = dict(solver=solver, tol=args.tol)
+        t_arr, xs = time_calls(lambda: apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw))
+        e2e_arrays = {"value": 9.0 * n * n / t_arr, "unit": "T-entries/s", "seconds_per_step": t_arr, "steps": args.steps,
+                      "api": "magpylib_material_response_b200.demag.apply_demag_arrays (host numpy in/out)",
+                      "max_abs_diff_vs_device_path": float(np.abs(rot.apply(xs) - x_dev).max())}
+        t0 = time.perf_counter()
+        coll = make_collection(name)
+        t_mesh = time.perf_counter() - t0
+        if coll is not None:
+            t_obj, solved = time_calls(lambda: apply_demag(coll, **kw))
+            pol_obj = collection_polarizations(solved)
+            e2e = {"value": 9.0 * n * n / t_obj, "unit": "T-entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "seconds_per_step": t_obj, "steps": args.steps, "timer": "time.perf_counter between synchronizes, max over ranks",
+                   "api": "apply_demag(collection) -- reference signature (demag.py:324-333) on mesh_Cuboid objects; returns the "
+                          "solved copy (inplace=False); Collection.copy(), gather, H2D, assembly, LU, D2H and write-back are inside",
+                   "mesh_Cuboid_s": t_mesh, "object_api_overhead_s": t_obj - t_step,
+                   "max_abs_diff_vs_device_path": float(np.abs(rot.apply(pol_obj) - x_dev).max())}
+        else:
+            e2e = dict(e2e_arrays, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h)
+
+    # ---- BASELINE configs[3] on the ranks of this run (N >= 2) -------------------------------------
+    config4 = None
+    if world > 1 and not args.no_config4 and solver == "lu":
+        del d_x, ipiv
+        config4 = run_config4(ctx, world, rank, dist)
+    elif world == 1:
+        config4 = {"skipped": "64 000 cells = 295 GB of Q: needs >= 2 GPUs (run by bench.py --gpus N, N >= 2)"}
 
     if rank != 0:
         if world > 1:
@@ -422,17 +690,16 @@ def run_ours(args):
     gemm_ms, gemm_flops, gemm_cnt = prof["gemm"]
     mv_ms, mv_bytes, mv_cnt = prof["matvec"]
     fpp = FLOP_PER_PAIR_ROTATED if rotated else FLOP_PER_PAIR_ALIGNED
+    ncu_pipe = traffic.get("assemble_cell_major", {}).get("fp64_pipe_frac_rotated" if rotated else "fp64_pipe_frac")
     roof_asm = {"bound": "fp64", "achieved": asm_pairs * fpp / (asm_ms * 1e-3) / 1e12 if asm_ms else None,
-                "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s (flop-equivalents, SURVEY 8d convention)",
+                "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s (flop-equivalents of the reference algorithm, SURVEY 8d convention)",
+                "frac": ncu_pipe, "frac_src": "ncu sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of this kernel "
+                                              "(profiles/, see ncu_traffic_r1.json); NOT achieved/peak: the far-field path evaluates "
+                                              "3 atan2 + 3 log per pair where the reference algorithm counts 24 + 6",
                 "traffic": traffic.get("assemble_cell_major", {}).get("ratio", 0) * 72.0 * asm_pairs / max(1, asm_cnt) or None,
                 "traffic_src": "72 B/pair x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
-                "note": "achieved counts the REFERENCE algorithm's work per pair (SURVEY 8d convention: 8 sqrt, 6 log, 24 atan2); "
-                        "the far-field path evaluates 3 atan2 + 3 log instead, so this can exceed the pipe peak. "
-                        "ncu: sm__pipe_fp64_cycles_active 53% (profiles/ncu_full_r1_summary.txt)",
                 "kernel": "assemble_cell_major_kernel", "ms_per_launch": asm_ms / max(1, asm_cnt),
                 "entries_per_s": 9.0 * asm_pairs / (asm_ms * 1e-3) if asm_ms else None, "peak_src": peaks["fp64_src"]}
-    if roof_asm["achieved"]:
-        roof_asm["frac"] = roof_asm["achieved"] / roof_asm["peak"]
     k_update = 256 if world == 1 else 3 * tgt_block  # rank of the trailing updates (two 128-column panels / one ownership block)
     if solver == "lu" and gemm_ms:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
@@ -440,9 +707,9 @@ def run_ours(args):
                     "frac": ach / peaks["fp64_dmma_tflops"],
                     "traffic": traffic.get("dgemm_nn", {}).get("ratio", 0) * (gemm_flops * 8.0 / k_update) / gemm_cnt or None,
                     "traffic_src": f"C read+write bytes (16 B per C element = flops*8/k, rank-{k_update} updates) x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
-                    "kernel": "dgemm_nn_fast_kernel (LU trailing update, DMMA.8x8x4)",
+                    "kernel": "LU trailing update (DMMA.8x8x4 GEMM)",
                     "launches": gemm_cnt, "ms_per_launch": gemm_ms / gemm_cnt,
-                    "peak_src": "FP64 DMMA peak " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry"}
+                    "peak_src": "FP64 DMMA peak: " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry"}
     elif mv_ms:
         ach = mv_bytes / (mv_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
@@ -453,31 +720,33 @@ def run_ours(args):
 
     stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps} for k, v in prof.items() if v[2]}
     lu_flops = (2.0 / 3.0) * N**3
-    lu_ms = sum(prof[k][0] for k in ("gemm", "panel", "trsm", "laswp", "panel_gemm")) / args.steps
-    if world > 1 or True:
-        # stages overlap (look-ahead) / are per rank: use the step time minus assembly and the solve
-        lu_ms = t_step * 1e3 - (prof["assemble"][0] + prof["trisolve"][0]) / args.steps
+    # stages overlap (look-ahead) / are per rank: use the step time minus assembly and the solve
+    lu_ms = t_step * 1e3 - (prof["assemble"][0] + prof["trisolve"][0]) / args.steps
+    worst_parity = max((r["max_rel_err"] for r in parity), default=None) if parity else None
     line = {
         "metric": "apply_demag_T_entries_per_s", "value": 9.0 * n * n / t_step, "unit": "T-entries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "desc": w["desc"], "n_cells": n, "matrix_order": N, "solver": solver,
-                   "row_block_cells": tgt_block, "l2": "inputs larger than L2 (Q is %.1f GB)" % (8.0 * N * ld / 1e9)
-                   if flush is None else "256 MB flush buffer written before every step"},
+        "parity_check": parity, "relres_check": relres, "config4": config4,
         "apply_demag_s": t_step,
         "assembly_entries_per_s": roof_asm["entries_per_s"],
         "lu_factor_tflops": lu_flops / (lu_ms * 1e-3) / 1e12 if (solver == "lu" and lu_ms) else None,
-        "gmres": {"iters": gm[0], "relres": gm[1]} if gm else None,
-        "relres_check": relres,
-        "stages": stages,
-        "roofline": roofline,
-        "roofline_assembly": roof_asm,
-        "e2e": e2e,
+        "e2e": e2e, "e2e_arrays": e2e_arrays,
         "gpu_launches": launches,
+        "config": bench_config(name, w, solver),
+        "sharding": {"row_block_cells": tgt_block, "ranks": world, "scheme": "block-cyclic target-row blocks" if world > 1 else "single GPU"},
+        "gmres": {"iters": gm[0], "relres": gm[1]} if gm else None,
+        "roofline": roofline,
         "clocks": clocks,
+        "stages": stages,
+        "roofline_assembly": roof_asm,
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(name)
+    # the facts a truncated tail must still show
+    line["summary"] = {"n_gpus": world, "ms_per_step": t_step * 1e3, "parity_max_rel_err": worst_parity, "relres_check": relres,
+                       "config4_apply_demag_s": (config4 or {}).get("apply_demag_s"), "config4_relres": (config4 or {}).get("relres"),
+                       "e2e_object_api_s": (e2e or {}).get("seconds_per_step"), "roofline_frac": roofline.get("frac")}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -496,6 +765,8 @@ def main():
     ap.add_argument("--restart", type=int, default=300, help="GMRES restart length")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiler runs only)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against the oracle")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 64 000-cell step that follows the timed region at N >= 2")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

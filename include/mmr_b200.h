@@ -86,6 +86,11 @@ int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
 /* Individual record durations (ms) of one class, in launch order; returns the count written. */
 int64_t mmr_ctx_profile_records(mmr_ctx* ctx, int kind, double* ms_out, int64_t cap);
 
+/* FP64 roofline denominators of this device, measured now (about 0.1 s): the FMA-pipe peak that bounds
+ * the assembly kernel and the tensor-pipe (DMMA.8x8x4) peak that bounds the LU trailing update, in
+ * TFLOP/s (MEASURED_PEAKS.json has no FP64 entry).  Host pointers, may be NULL. */
+int mmr_fp64_peaks(mmr_ctx* ctx, double* fma_tflops_out, double* dmma_tflops_out);
+
 /* ---- kernel 1: demag tensor assembly (demag.py:124-224 + :451-452 + :466) ------------- */
 /*
  * Evaluates the analytic cuboid H-field block of every source cell i in [src_begin,src_end)
@@ -125,6 +130,15 @@ int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos, const dou
                          const double* d_dim, const int32_t* d_cls, const double* d_chi,
                          double* d_out, int64_t ld, int64_t table_cap_slots,
                          int64_t* n_unique_out);
+
+/* The same for a row shard (multi-GPU): only the n_tgt_local targets of the block-cyclic target set
+ * (tgt_block, tgt_nparts, tgt_part), as in mmr_assemble; rows of d_out are the local targets.  The unique-pair
+ * table covers this shard's pairs, so a class representative is the smallest flat index i*n+j among them. */
+int mmr_assemble_matched_rows(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
+                              const double* d_dim, const int32_t* d_cls, const double* d_chi,
+                              double* d_out, int64_t ld, int64_t table_cap_slots, int64_t n_tgt_local,
+                              int64_t tgt_block, int64_t tgt_nparts, int64_t tgt_part,
+                              int64_t* n_unique_out);
 
 /* ---- kernel 2a: dense LU with partial pivoting (np.linalg.solve / dgesv, demag.py:470) -- */
 /*
@@ -211,6 +225,13 @@ int mmr_gmres_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_blo
  */
 int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block,
                       double* d_Qlocal, int64_t ld, double* d_b, int* info_out);
+/* The two phases of mmr_lu_solve_dist on their own, so that a factorized (sharded) system can be kept
+ * and solved again for further right-hand sides (apply_demag's demag_store on several GPUs):
+ * d_ipiv (N int32, device) receives / provides the replicated pivot sequence. */
+int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block,
+                       double* d_Qlocal, int64_t ld, int32_t* d_ipiv_out, int* info_out);
+int mmr_lu_trisolve_dist(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block,
+                         const double* d_Qlocal, int64_t ld, const int32_t* d_ipiv, double* d_b);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ _SIGNATURES = {
         ctypes.c_int64,
         [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int64],
     ),
+    "mmr_fp64_peaks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "mmr_assemble": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]
@@ -63,6 +64,12 @@ _SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p, ctypes.c_void_p,
          _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
+    ),
+    "mmr_assemble_matched_rows": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p, ctypes.c_void_p,
+         _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+         ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
     ),
     "mmr_lu_factor": (
         ctypes.c_int,
@@ -113,6 +120,16 @@ _SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64,
          _c_double_p, ctypes.POINTER(ctypes.c_int)],
+    ),
+    "mmr_lu_factor_dist": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64,
+         ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)],
+    ),
+    "mmr_lu_trisolve_dist": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64,
+         ctypes.c_void_p, _c_double_p],
     ),
 }
 
@@ -248,6 +265,12 @@ class Context:
         n = self.lib.mmr_ctx_profile_records(self.handle, self.PROF_KINDS.index(kind), buf, cap)
         return list(buf[:n])
 
+    def fp64_peaks(self):
+        """(FMA-pipe TFLOP/s, DMMA tensor-pipe TFLOP/s) of this device, measured now."""
+        fma, mma = ctypes.c_double(0), ctypes.c_double(0)
+        _check(self.lib, self.lib.mmr_fp64_peaks(self.handle, ctypes.byref(fma), ctypes.byref(mma)))
+        return fma.value, mma.value
+
     # ---- kernel 1 --------------------------------------------------------------------
     def assemble(self, pos, quat, dim, out, ld, *, chi=None, max_dist=0.0, layout=LAYOUT_CELL_MAJOR,
                  src_range=None, tgt_first=0, n_tgt_local=None, tgt_block=None, tgt_nparts=1,
@@ -266,12 +289,17 @@ class Context:
             ),
         )
 
-    def assemble_matched(self, pos, quat, dim, cls, out, ld, *, chi=None, table_cap_slots=1 << 24):
+    def assemble_matched(self, pos, quat, dim, cls, out, ld, *, chi=None, table_cap_slots=1 << 24,
+                         n_tgt_local=None, tgt_block=None, tgt_nparts=1, tgt_part=0):
+        """pairs_matching assembly; with n_tgt_local / tgt_block / tgt_nparts / tgt_part only the rows of
+        this rank's block-cyclic target set (multi-GPU)."""
         n = pos.shape[0]
         nuniq = ctypes.c_int64(0)
-        status = self.lib.mmr_assemble_matched(
+        if n_tgt_local is None:
+            n_tgt_local, tgt_block = n, max(1, n)
+        status = self.lib.mmr_assemble_matched_rows(
             self.handle, n, _ptr(pos), _ptr(quat), _ptr(dim), _ptr(cls), _ptr(chi), _ptr(out), ld,
-            table_cap_slots, ctypes.byref(nuniq),
+            table_cap_slots, n_tgt_local, tgt_block, tgt_nparts, tgt_part, ctypes.byref(nuniq),
         )
         if status == -3:
             return None
@@ -352,6 +380,17 @@ class Context:
         return info.value
 
 
+    def lu_factor_dist(self, N, nrows_local, tgt_block, Qlocal, ld, ipiv):
+        info = ctypes.c_int(0)
+        _check(self.lib, self.lib.mmr_lu_factor_dist(self.handle, N, nrows_local, tgt_block, _ptr(Qlocal), ld,
+                                                     _ptr(ipiv), ctypes.byref(info)))
+        return info.value
+
+    def lu_trisolve_dist(self, N, nrows_local, tgt_block, Qlocal, ld, ipiv, b):
+        _check(self.lib, self.lib.mmr_lu_trisolve_dist(self.handle, N, nrows_local, tgt_block, _ptr(Qlocal), ld,
+                                                       _ptr(ipiv), _ptr(b)))
+
+
 _default_ctx = {}
 
 
@@ -366,8 +405,19 @@ def default_context(device=None):
         )
         raise NativeUnavailableError(msg)
     idx = torch.cuda.current_device() if device is None else int(device)
-    ctx = _default_ctx.get(idx)
+    # one context per (device, torch current stream): the torch copies / allocations around a native call
+    # run on the current stream, so the kernels must be enqueued there too (inside `with
+    # torch.cuda.stream(s)` the legacy default stream would be unordered with them)
+    stream = torch.cuda.current_stream(idx)
+    key = (idx, stream.cuda_stream)
+    ctx = _default_ctx.get(key)
     if ctx is None:
-        ctx = Context(idx, torch.cuda.default_stream(idx))
-        _default_ctx[idx] = ctx
+        ctx = Context(idx, stream)
+        if key[1] != 0:
+            # communicator state is per process group, not per stream: share the default-stream context's
+            base = _default_ctx.get((idx, 0))
+            if base is not None and base.nranks > 1:
+                msg = "multi-GPU calls must be made on the default stream (the NCCL communicator lives in that context)"
+                raise NativeError(-1, msg)
+        _default_ctx[key] = ctx
     return ctx

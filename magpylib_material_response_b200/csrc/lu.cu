@@ -1758,16 +1758,42 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
-extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local, int64_t tgt_block,
-                                 double* d_Qlocal, int64_t ld, double* d_b, int* info_out) {
+static int dist_check_args(mmr_ctx* ctx, int64_t N64, int64_t nrows_local, int64_t tgt_block, const double* d_Qlocal,
+                           int64_t ld) {
   MMR_ARG(ctx != nullptr, "ctx is NULL");
   MMR_ARG(N64 >= 0 && N64 < (1LL << 31) && N64 % 3 == 0, "N out of range / not a multiple of 3");
   MMR_ARG(ld >= N64 && tgt_block >= 1 && nrows_local >= 0, "bad sizes");
   MMR_ARG(3 * tgt_block <= 2 * NB, "distributed LU needs 3*tgt_block <= 256");
   MMR_ARG(ctx->nranks == 1 || ctx->nccl_comm != nullptr, "communicator not initialised");
+  MMR_ARG(d_Qlocal || nrows_local == 0 || N64 == 0, "NULL pointer");
+  return 0;
+}
+
+extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local, int64_t tgt_block,
+                                 double* d_Qlocal, int64_t ld, double* d_b, int* info_out) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
   if (info_out) *info_out = 0;
   if (N64 == 0) return 0;
-  MMR_ARG(d_b && (d_Qlocal || nrows_local == 0), "NULL pointer");
+  MMR_ARG(d_b != nullptr, "NULL right-hand side");
+  // pivots of this call live behind the factorization's workspace
+  // (pivots + the solve phase's permutation and copy of b, so that mmr_lu_trisolve_dist does not have to grow it)
+  int rc = mmr_ws2_reserve(ctx, 2 * (sizeof(int) * (size_t)N64 + 512) + sizeof(double) * (size_t)N64 + 512);
+  if (rc) return rc;
+  int32_t* d_ipiv = (int32_t*)ctx->ws2;
+  rc = mmr_lu_factor_dist(ctx, N64, nrows_local, tgt_block, d_Qlocal, ld, d_ipiv, info_out);
+  if (rc) return rc;
+  return mmr_lu_trisolve_dist(ctx, N64, nrows_local, tgt_block, d_Qlocal, ld, d_ipiv, d_b);
+}
+
+extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local, int64_t tgt_block,
+                                  double* d_Qlocal, int64_t ld, int32_t* d_ipiv_out, int* info_out) {
+  {
+    const int rc0 = dist_check_args(ctx, N64, nrows_local, tgt_block, d_Qlocal, ld);
+    if (rc0) return rc0;
+  }
+  if (info_out) *info_out = 0;
+  if (N64 == 0) return 0;
+  MMR_ARG(d_ipiv_out != nullptr, "NULL pivot pointer");
   DeviceGuard g(ctx->device);
   const int N = (int)N64;
   const int R = ctx->nranks, me = ctx->rank;
@@ -1788,17 +1814,15 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
   }
   bool spec_on = spec_default != 0;
 
-  // workspace: [info | strip scratch | spec scratch | ipiv | 2 x broadcast record | spec panel | tmp]
+  // workspace: [info | strip scratch | spec scratch | 2 x broadcast record | spec panel]
   // broadcast record of an outer block: header (L11^-1 of both panels, the block's pivots) + packed
   // panel (m x ob, ld = m): ONE ncclBroadcast per outer block.
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
   const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
-  const size_t ipiv_bytes = ((sizeof(int) * (size_t)N + 255) / 256) * 256;
   const size_t hdr_doubles = 2 * (size_t)NB * NB + NB;  // + 2*NB ints
   const size_t rec_bytes = ((sizeof(double) * (hdr_doubles + (size_t)N * obw) + 255) / 256) * 256;
   const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256) * 256 : 0;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + spec_bytes + ipiv_bytes + 2 * rec_bytes + sbuf_bytes +
-                                   sizeof(double) * (size_t)N + 512);
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + spec_bytes + 2 * rec_bytes + sbuf_bytes + 512);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
   if (rc) return rc;
@@ -1806,11 +1830,10 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
   int* d_info = (int*)base;
   void* scratch = base + 256;
   void* d_spec = base + 256 + scratch_bytes;
-  int* d_ipiv = (int*)(base + 256 + scratch_bytes + spec_bytes);
-  double* rec[2] = {(double*)(base + 256 + scratch_bytes + spec_bytes + ipiv_bytes),
-                    (double*)(base + 256 + scratch_bytes + spec_bytes + ipiv_bytes + rec_bytes)};
-  double* Sbuf = (double*)(base + 256 + scratch_bytes + spec_bytes + ipiv_bytes + 2 * rec_bytes);
-  double* d_tmp = (double*)((char*)Sbuf + sbuf_bytes);
+  int* d_ipiv = d_ipiv_out;
+  double* rec[2] = {(double*)(base + 256 + scratch_bytes + spec_bytes),
+                    (double*)(base + 256 + scratch_bytes + spec_bytes + rec_bytes)};
+  double* Sbuf = (double*)(base + 256 + scratch_bytes + spec_bytes + 2 * rec_bytes);
   auto LinvOf = [&](int s, int inner) { return rec[s & 1] + (size_t)inner * NB * NB; };
   auto IpivOf = [&](int s) { return (int*)(rec[s & 1] + 2 * (size_t)NB * NB); };
   auto PanelOf = [&](int s) { return rec[s & 1] + hdr_doubles; };
@@ -1958,9 +1981,54 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
       if (rc) return rc;
     }
   }
-  // the solves below run on the main stream only, after everything on the side stream
+  // whatever follows on the main stream comes after everything on the side stream
   MMR_CUDA(cudaEventRecord(ctx->ev[0], side));
   MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[0], 0));
+  int* h_info = (int*)ctx->hpin;
+  MMR_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MMR_CUDA(cudaStreamSynchronize(st));
+  if (info_out) *info_out = *h_info;  // only the owner of a zero pivot sees it; callers reduce over ranks
+  return 0;
+}
+
+// Triangular solves with the distributed factors of mmr_lu_factor_dist (d_ipiv: the N replicated pivots it
+// returned): U^T w = b, L^T v = w, x = P v.  d_b (N, replicated) is overwritten by x on every rank.
+extern "C" int mmr_lu_trisolve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local, int64_t tgt_block,
+                                    const double* d_Qlocal, int64_t ld, const int32_t* d_ipiv, double* d_b) {
+  {
+    const int rc0 = dist_check_args(ctx, N64, nrows_local, tgt_block, d_Qlocal, ld);
+    if (rc0) return rc0;
+  }
+  if (N64 == 0) return 0;
+  MMR_ARG(d_b && d_ipiv, "NULL pointer");
+  DeviceGuard g(ctx->device);
+  const int N = (int)N64;
+  const int R = ctx->nranks, me = ctx->rank;
+  const int obw = (int)(3 * tgt_block);
+  const int S = (int)ceil_div64(N, obw);
+  cudaStream_t st = ctx->stream;
+  const double* Al = d_Qlocal;
+  int rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
+  if (rc) return rc;
+  // scratch of the solve phase lives in ws2 BEHIND the pivots mmr_lu_solve_dist keeps there
+  const size_t off = ((sizeof(int) * (size_t)N + 256 + 255) / 256) * 256;
+  const size_t perm_bytes = ((sizeof(int) * (size_t)N + 255) / 256) * 256;
+  if (ctx->ws2_bytes < off + perm_bytes + sizeof(double) * (size_t)N) {
+    // growing ws2 would free the pivots when they live there: stage them through the pinned buffer
+    const bool inside = (const char*)d_ipiv >= (const char*)ctx->ws2 && (const char*)d_ipiv < (const char*)ctx->ws2 + ctx->ws2_bytes;
+    if (inside) {
+      MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+      MMR_CUDA(cudaStreamSynchronize(st));
+    }
+    rc = mmr_ws2_reserve(ctx, off + perm_bytes + sizeof(double) * (size_t)N);
+    if (rc) return rc;
+    if (inside) {
+      MMR_CUDA(cudaMemcpyAsync(ctx->ws2, ctx->hpin, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+      d_ipiv = (const int32_t*)ctx->ws2;
+    }
+  }
+  int* d_perm = (int*)((char*)ctx->ws2 + off);
+  double* d_tmp = (double*)((char*)ctx->ws2 + off + perm_bytes);
 
   // ---- triangular solves, block by block (each block in two <= 128-row steps) -----------------
   const size_t diag_smem = (size_t)SB * (SB + 1) * sizeof(double);
@@ -2016,9 +2084,7 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
   int* h_ipiv = (int*)ctx->hpin;
   int* h_perm = h_ipiv + N;
   MMR_CUDA(cudaMemcpyAsync(h_ipiv, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
-  MMR_CUDA(cudaMemcpyAsync(h_perm, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
   MMR_CUDA(cudaStreamSynchronize(st));
-  const int info = h_perm[0];
   for (int i = 0; i < N; ++i) h_perm[i] = i;
   for (int i = N - 1; i >= 0; --i) {
     const int p = h_ipiv[i];
@@ -2028,12 +2094,10 @@ extern "C" int mmr_lu_solve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local,
       h_perm[p] = t;
     }
   }
-  int* d_perm = d_ipiv;  // pivots no longer needed on the device
   MMR_CUDA(cudaMemcpyAsync(d_perm, h_perm, sizeof(int) * N, cudaMemcpyHostToDevice, st));
   MMR_CUDA(cudaMemcpyAsync(d_tmp, d_b, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
   lu_gather_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(d_tmp, d_perm, N, d_b);
   MMR_CHECK_LAUNCH(ctx);
   MMR_CUDA(cudaStreamSynchronize(st));
-  if (info_out) *info_out = info;  // only the owner of a zero pivot sees it; callers reduce over ranks
   return 0;
 }

@@ -39,7 +39,14 @@ struct MatchParams {
   u64 mask;        // capacity - 1 (capacity is a power of two)
   int* status;     // [0] = number of classes, [1] = overflow flag, [2] = key out of range
   int rotated;
+  // target set of this rank (block-cyclic over cells, as mmr_assemble): local target t is global cell
+  // ((t / tgt_block) * tgt_nparts + tgt_part) * tgt_block + t % tgt_block; rows of `out` are local targets
+  int64_t n_tgt_local, tgt_block, tgt_nparts, tgt_part;
 };
+
+__device__ __forceinline__ int64_t global_target(const MatchParams& p, int64_t t) {
+  return ((t / p.tgt_block) * p.tgt_nparts + p.tgt_part) * p.tgt_block + t % p.tgt_block;
+}
 
 struct PairKey {
   u64 lo, hi;  // lo = kx | ky << 32, hi = kz | cls << 32 | valid bit 63
@@ -83,7 +90,7 @@ __device__ __forceinline__ void cas128(u64* addr, u64 new_lo, u64 new_hi, u64& o
 template <bool INSERT>
 __device__ __forceinline__ u64 find_slot(const MatchParams& p, const PairKey& key, u64 me) {
   u64 h = hash_key(key) & p.mask;
-  for (u64 probes = 0; probes <= p.mask; ++probes) {
+  for (long long probes = 0; probes <= (long long)p.mask; ++probes) {
     const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(p.tab + 2 * h));  // L2: where the CAS lands
     u64 lo = cur.x, hi = cur.y;
     if (hi == 0) {  // empty (a valid key has bit 63 of hi set)
@@ -99,6 +106,13 @@ __device__ __forceinline__ u64 find_slot(const MatchParams& p, const PairKey& ke
       if (INSERT && me < p.minrep[h]) atomicMin(&p.minrep[h], me);
       return h;
     }
+    if (hi == key.hi && lo == 0 && key.lo != 0) {
+      // the 16-byte vector load is not guaranteed single-copy atomic against the 128-bit CAS that
+      // publishes a slot: a reader can see the new `hi` with a stale (zero) `lo`.  Look again instead
+      // of walking past a slot that may hold this very key (which would insert it a second time).
+      --probes;
+      continue;
+    }
     h = (h + 1) & p.mask;
   }
   return ~0ull;
@@ -108,8 +122,9 @@ __device__ __forceinline__ u64 find_slot(const MatchParams& p, const PairKey& ke
 __global__ void __launch_bounds__(256) match_insert_kernel(const MatchParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
-  for (int64_t j = blockIdx.y; j < p.n; j += gridDim.y) {
+  for (int64_t t = blockIdx.y; t < p.n_tgt_local; t += gridDim.y) {
     if (p.status[1] | p.status[2]) return;
+    const int64_t j = global_target(p, t);
     const PairKey key = make_key(p, i, j);
     if (!key.ok) {
       atomicExch(&p.status[2], 1);
@@ -117,7 +132,7 @@ __global__ void __launch_bounds__(256) match_insert_kernel(const MatchParams p) 
     }
     const u64 h = find_slot<true>(p, key, (u64)(i * p.n + j));
     if (h == ~0ull) atomicExch(&p.status[1], 1);
-    else if (p.slot_of_pair) p.slot_of_pair[j * p.n + i] = (unsigned)h;
+    else if (p.slot_of_pair) p.slot_of_pair[t * p.n + i] = (unsigned)h;
     // load factor guard: stop early once the table is more than half full
     if (threadIdx.x == 0 && (u64)p.status[0] * 2 > p.mask + 1) atomicExch(&p.status[1], 1);
   }
@@ -163,11 +178,12 @@ __global__ void __launch_bounds__(SRC_TILE) match_scatter_kernel(const MatchPara
   __shared__ double s_stage[SRC_TILE / 32][3][96];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t0 = (int64_t)blockIdx.y * TGT_TILE;
-  const int ntgt = (int)min((int64_t)TGT_TILE, p.n - t0);
+  const int ntgt = (int)min((int64_t)TGT_TILE, p.n_tgt_local - t0);
   if (FUSE_Q && tid < ntgt) {
-    s_tchi[tid][0] = p.chi[3 * (t0 + tid) + 0];
-    s_tchi[tid][1] = p.chi[3 * (t0 + tid) + 1];
-    s_tchi[tid][2] = p.chi[3 * (t0 + tid) + 2];
+    const int64_t jg = global_target(p, t0 + tid);
+    s_tchi[tid][0] = p.chi[3 * jg + 0];
+    s_tchi[tid][1] = p.chi[3 * jg + 1];
+    s_tchi[tid][2] = p.chi[3 * jg + 2];
   }
   const int64_t i_warp0 = (int64_t)blockIdx.x * SRC_TILE + warp * 32;
   const int64_t i = i_warp0 + lane;
@@ -175,8 +191,8 @@ __global__ void __launch_bounds__(SRC_TILE) match_scatter_kernel(const MatchPara
   __syncthreads();
   const int64_t ncols_warp = min((int64_t)96, 3 * (p.n - i_warp0));
   for (int tt = 0; tt < ntgt; ++tt) {
-    const int64_t j = t0 + tt;
-    const u64 h = p.slot_of_pair ? (u64)p.slot_of_pair[j * p.n + ic]
+    const int64_t j = global_target(p, t0 + tt);
+    const u64 h = p.slot_of_pair ? (u64)p.slot_of_pair[(t0 + tt) * p.n + ic]
                                  : find_slot<false>(p, make_key(p, ic, j), 0ull);
     double blk[9];
     {
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(SRC_TILE) match_scatter_kernel(const MatchPara
 #pragma unroll
       for (int k = 0; k < 3; ++k) s_stage[warp][l][3 * lane + k] = blk[3 * l + k];
     __syncwarp();
-    double* row_base = p.out + (3 * j) * p.ld + 3 * i_warp0;
+    double* row_base = p.out + (3 * (t0 + tt)) * p.ld + 3 * i_warp0;
 #pragma unroll
     for (int l = 0; l < 3; ++l)
 #pragma unroll
@@ -228,13 +244,28 @@ extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos
                                     const double* d_dim, const int32_t* d_cls, const double* d_chi,
                                     double* d_out, int64_t ld, int64_t table_cap_slots,
                                     int64_t* n_unique_out) {
+  return mmr_assemble_matched_rows(ctx, n, d_pos, d_quat, d_dim, d_cls, d_chi, d_out, ld, table_cap_slots, n, n > 0 ? n : 1, 1,
+                                   0, n_unique_out);
+}
+
+extern "C" int mmr_assemble_matched_rows(mmr_ctx* ctx, int64_t n, const double* d_pos, const double* d_quat,
+                                         const double* d_dim, const int32_t* d_cls, const double* d_chi,
+                                         double* d_out, int64_t ld, int64_t table_cap_slots, int64_t n_tgt_local,
+                                         int64_t tgt_block, int64_t tgt_nparts, int64_t tgt_part,
+                                         int64_t* n_unique_out) {
   MMR_ARG(ctx != nullptr, "ctx is NULL");
   MMR_ARG(n >= 0, "negative n");
   if (n_unique_out) *n_unique_out = 0;
-  if (n == 0) return 0;
+  if (n == 0 || n_tgt_local == 0) return 0;
   MMR_ARG(d_pos && d_quat && d_dim && d_cls && d_out, "NULL pointer");
   MMR_ARG(ld >= 3 * n, "ld must be >= 3*n");
   MMR_ARG(table_cap_slots >= 2, "table_cap_slots too small");
+  MMR_ARG(n_tgt_local > 0 && tgt_block >= 1 && tgt_nparts >= 1 && tgt_part >= 0 && tgt_part < tgt_nparts, "bad target set");
+  {
+    const int64_t last = n_tgt_local - 1;
+    const int64_t jlast = ((last / tgt_block) * tgt_nparts + tgt_part) * tgt_block + last % tgt_block;
+    MMR_ARG(jlast < n, "target set exceeds n");
+  }
   DeviceGuard g(ctx->device);
   int rc = mmr_ws_reserve(ctx, 256);
   if (rc) return rc;
@@ -245,7 +276,7 @@ extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos
   if (rc) return rc;
 
   // capacity: power of two, grown on overflow up to table_cap_slots (88 B per slot)
-  const u64 npairs = (u64)n * (u64)n;
+  const u64 npairs = (u64)n * (u64)n_tgt_local;
   u64 cap = 1ull << 16;
   while (cap < (1ull << 21) && cap < 4 * npairs) cap <<= 1;
   // one slot id per pair, so the scatter pass needs no second lookup (skipped beyond 12 GB)
@@ -266,10 +297,11 @@ extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos
     p.slot_of_pair = slot_bytes ? (unsigned*)(base + tab_bytes) : nullptr;
     p.mask = cap - 1;
     p.rotated = rotated;
+    p.n_tgt_local = n_tgt_local; p.tgt_block = tgt_block; p.tgt_nparts = tgt_nparts; p.tgt_part = tgt_part;
     MMR_CUDA(cudaMemsetAsync(p.status, 0, 256, ctx->stream));
     MMR_CUDA(cudaMemsetAsync(p.tab, 0, sizeof(u64) * 2 * cap, ctx->stream));
     MMR_CUDA(cudaMemsetAsync(p.minrep, 0xff, sizeof(u64) * cap, ctx->stream));
-    dim3 gi((unsigned)ceil_div64(n, 256), (unsigned)(n < 2048 ? n : 2048));
+    dim3 gi((unsigned)ceil_div64(n, 256), (unsigned)(n_tgt_local < 2048 ? n_tgt_local : 2048));
     match_insert_kernel<<<gi, 256, 0, ctx->stream>>>(p);
     MMR_CHECK_LAUNCH(ctx);
     MMR_CUDA(cudaMemcpyAsync(ctx->hpin, p.status, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -291,13 +323,21 @@ extern "C" int mmr_assemble_matched(mmr_ctx* ctx, int64_t n, const double* d_pos
     }
     match_eval_kernel<<<(unsigned)ceil_div64((int64_t)cap, 128), 128, 0, ctx->stream>>>(p);
     MMR_CHECK_LAUNCH(ctx);
-    dim3 gs((unsigned)ceil_div64(n, SRC_TILE), (unsigned)ceil_div64(n, TGT_TILE));
+    dim3 gs((unsigned)ceil_div64(n, SRC_TILE), (unsigned)ceil_div64(n_tgt_local, TGT_TILE));
     const int pidx = mmr_prof_begin(ctx, MMR_PROF_ASSEMBLE, ctx->stream);
     if (d_chi) match_scatter_kernel<true><<<gs, SRC_TILE, 0, ctx->stream>>>(p);
     else match_scatter_kernel<false><<<gs, SRC_TILE, 0, ctx->stream>>>(p);
-    mmr_prof_end(ctx, pidx, (double)n * (double)n, ctx->stream);
+    mmr_prof_end(ctx, pidx, (double)n * (double)n_tgt_local, ctx->stream);
     MMR_CHECK_LAUNCH(ctx);
     if (n_unique_out) *n_unique_out = nclasses;
+    // the per-pair slot record (4 B x n x n_tgt_local, up to 12 GB) is dead now: do not keep it for the
+    // lifetime of the process-wide context
+    if (slot_bytes > ((size_t)1 << 30)) {
+      MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+      MMR_CUDA(cudaFree(ctx->ws2));
+      ctx->ws2 = nullptr;
+      ctx->ws2_bytes = 0;
+    }
     return 0;
   }
 }

@@ -434,12 +434,87 @@ def _system_key(pos, quat, dim, chi, max_dist, solver):
     return f"{solver}:{len(pos)}:{h.hexdigest()}"
 
 
+def _solve_cells_sharded(ctx, pos, quat, dim, chi, rhs, *, pairs_matching, max_dist, split, solver, tol,
+                         min_log_time, demag_store):
+    """Multi-GPU form of ``solve_cells_global`` (one process per GPU, SPMD: every rank makes the same call
+    with the same host arrays and gets the full solution back).  This rank assembles and owns a
+    block-cyclic set of target-row blocks -- no exchange during assembly.  ``pairs_matching`` uses a
+    unique-pair table over this rank's rows, ``split`` tiles the sources, ``demag_store`` keeps the rank's
+    shard of the factorized system (LU factors + replicated pivots, or Q for GMRES) for later calls."""
+    from . import distributed as mdist
+
+    torch = ctx.torch
+    n = len(pos)
+    N = 3 * n
+    info = {"n_gpus": ctx.nranks}
+    tgt_block = mdist.DEFAULT_TGT_BLOCK
+    n_local = len(mdist.owned_cells(n, tgt_block, ctx.nranks, ctx.rank))
+    shard = dict(n_tgt_local=n_local, tgt_block=tgt_block, tgt_nparts=ctx.nranks, tgt_part=ctx.rank)
+    ld = _padded_ld(N)
+    key = None if demag_store is None else _system_key(pos, quat, dim, chi, max_dist, solver) + f":r{ctx.rank}/{ctx.nranks}"
+    cached = None if key is None else demag_store.get(key)
+    if cached is not None and cached["device"] != str(ctx.device):
+        cached = None
+    # every rank must take the same branch (the solves are collective)
+    flag = torch.tensor([0 if cached is None else 1], device=ctx.device)
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        cached = None
+    info["demag_store"] = None if demag_store is None else ("hit" if cached is not None else "miss")
+    with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):
+        if cached is not None:
+            Q = cached["Q"]
+        else:
+            d_pos, d_quat, d_dim = ctx.to_device(pos), ctx.to_device(quat), ctx.to_device(dim)
+            d_chi = ctx.to_device(np.asarray(chi, dtype=float).reshape(N))
+            Q = ctx.empty(3 * n_local, ld)
+            done = False
+            if pairs_matching and max_dist == 0 and n_local > 0:
+                cls = torch.from_numpy(_source_classes(quat, dim)).to(ctx.device)
+                nuniq = ctx.assemble_matched(d_pos, d_quat, d_dim, cls, Q, ld, chi=d_chi, **shard)
+                done = nuniq is not None
+                info["unique_pairs_this_rank"] = nuniq
+            if not done:
+                s0 = 0
+                for cnt in (len(c) for c in np.array_split(np.arange(n), max(1, int(split)))):
+                    if cnt:
+                        ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, max_dist=max_dist,
+                                     src_range=(s0, s0 + cnt), **shard)
+                    s0 += cnt
+    with timelog("Solving of linear system", min_log_time=min_log_time):
+        d_x = ctx.to_device(rhs)
+        if solver == "lu":
+            if cached is not None:
+                ipiv = cached["ipiv"]
+            else:
+                ipiv = ctx.empty(N, dtype=torch.int32)
+                lu_info = ctx.lu_factor_dist(N, 3 * n_local, tgt_block, Q, ld, ipiv)
+                flag = torch.tensor([lu_info], device=ctx.device)
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                if int(flag.item()) != 0:
+                    msg = f"Singular matrix (zero pivot at elimination step {int(flag.item())})"
+                    raise np.linalg.LinAlgError(msg)
+                if key is not None:
+                    demag_store[key] = {"Q": Q, "ld": ld, "ipiv": ipiv, "device": str(ctx.device)}
+            ctx.lu_trisolve_dist(N, 3 * n_local, tgt_block, Q, ld, ipiv, d_x)
+        else:
+            if key is not None and cached is None:
+                demag_store[key] = {"Q": Q, "ld": ld, "device": str(ctx.device)}
+            d_b = d_x
+            d_x = torch.zeros_like(d_b)
+            iters, relres = ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_b, d_x, tol=tol,
+                                           restart=min(300, N), maxit=max(1000, 2 * N))
+            info["gmres_iters"], info["gmres_relres"] = iters, relres
+        x = d_x.cpu().numpy().reshape(n, 3)
+    return x, info
+
+
 def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching=False, max_dist=0,
                        split=1, solver="lu", tol=1e-12, device=None, min_log_time=None, demag_store=None):
     """Host arrays in, host array out: assemble Q = I - chi*N on the device, solve
     Q x = J0 + chi*H_ext (demag.py:444-470).  All (n,3) arrays, GLOBAL frame.  Returns (x, info).
 
-    ``demag_store`` (a dict, single GPU): the device-resident system of this geometry -- the LU
+    ``demag_store`` (a dict): the device-resident system of this geometry -- the LU
     factors and pivots for ``solver="lu"``, the assembled Q for ``"gmres"`` -- is kept in it and
     reused by later calls with bit-identical cells, chi and max_dist, which then only pay for the
     right-hand side (triangular solves: milliseconds instead of the O(n^3) factorization)."""
@@ -452,35 +527,9 @@ def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching
     info = {}
     rhs = (np.asarray(pol_global, dtype=float) + np.asarray(chi, dtype=float) * np.asarray(H_ext, dtype=float)).reshape(N)
     if mdist.ensure_comm(ctx) > 1:
-        # one process per GPU: this rank assembles and owns a block-cyclic set of target-row blocks
-        # (no exchange during assembly); every rank returns the full solution.
-        tgt_block = mdist.DEFAULT_TGT_BLOCK
-        n_local = len(mdist.owned_cells(n, tgt_block, ctx.nranks, ctx.rank))
-        ld = _padded_ld(N)
-        d_pos, d_quat, d_dim = ctx.to_device(pos), ctx.to_device(quat), ctx.to_device(dim)
-        d_chi = ctx.to_device(np.asarray(chi, dtype=float).reshape(N))
-        Q = ctx.empty(3 * n_local, ld)
-        with timelog("Demagnetization tensor calculation", min_log_time=min_log_time):
-            ctx.assemble(d_pos, d_quat, d_dim, Q, ld, chi=d_chi, max_dist=max_dist, n_tgt_local=n_local,
-                         tgt_block=tgt_block, tgt_nparts=ctx.nranks, tgt_part=ctx.rank)
-        with timelog("Solving of linear system", min_log_time=min_log_time):
-            d_x = ctx.to_device(rhs)
-            if solver == "lu":
-                lu_info = ctx.lu_solve_dist(N, 3 * n_local, tgt_block, Q, ld, d_x)
-                flag = torch.tensor([lu_info], device=ctx.device)
-                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
-                if int(flag.item()) != 0:
-                    msg = f"Singular matrix (zero pivot at elimination step {int(flag.item())})"
-                    raise np.linalg.LinAlgError(msg)
-            else:
-                d_b = d_x
-                d_x = torch.zeros_like(d_b)
-                iters, relres = ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_b, d_x, tol=tol,
-                                               restart=min(300, N), maxit=max(1000, 2 * N))
-                info["gmres_iters"], info["gmres_relres"] = iters, relres
-            x = d_x.cpu().numpy().reshape(n, 3)
-        info["n_gpus"] = ctx.nranks
-        return x, info
+        return _solve_cells_sharded(ctx, pos, quat, dim, chi, rhs, pairs_matching=pairs_matching, max_dist=max_dist,
+                                    split=split, solver=solver, tol=tol, min_log_time=min_log_time,
+                                    demag_store=demag_store)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     key = None if demag_store is None else _system_key(pos, quat, dim, chi, max_dist, solver)
     cached = None if key is None else demag_store.get(key)

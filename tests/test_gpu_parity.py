@@ -701,3 +701,92 @@ def test_lu_large_panel_fallback_path(ctx):
     ctx.matvec(Q0, ld, x, y)
     resid = float(torch.linalg.norm(y - b) / (torch.linalg.norm(Q0[:, :N]) * torch.linalg.norm(x)))
     assert resid < 1e-14, resid
+
+
+def test_pairs_matching_row_shards_tile_the_dense_matrix(ctx):
+    """Multi-GPU pairs_matching (mmr_assemble_matched_rows): each rank's unique-pair table covers its own
+    block-cyclic target rows; the union of the shards reproduces the dense matrix, and a shard's table is
+    smaller than the full one."""
+    from magpylib_material_response_b200.demag import _source_classes
+
+    parts = [oref.mesh_cuboid_arrays((1e-3,) * 3, (4, 4, 4), position=(1.5e-3 * ix, 0, 1.5e-3 * iz))
+             for ix in range(2) for iz in range(2)]
+    pos, quat, dim = (np.vstack([p[k] for p in parts]) for k in range(3))
+    n, N = len(pos), 3 * len(pos)
+    chi = np.tile((0.3, 0.2, 0.1), n)
+    cls = torch.from_numpy(_source_classes(quat, dim)).to(ctx.device)
+    d_pos, d_quat, d_dim, d_chi = (dev(ctx, a) for a in (pos, quat, dim, chi))
+    dense = assemble_numpy(ctx, pos, quat, dim, chi_cell_major=chi)
+    ld = N + 8
+    full = ctx.empty(N, ld)
+    nuniq_full = ctx.assemble_matched(d_pos, d_quat, d_dim, cls, full, ld, chi=d_chi)
+    tgt_block, nparts = 24, 3
+    nblk = -(-n // tgt_block)
+    rebuilt = np.zeros_like(dense)
+    for part in range(nparts):
+        cells = np.concatenate([np.arange(b * tgt_block, min(n, (b + 1) * tgt_block)) for b in range(part, nblk, nparts)])
+        out = ctx.empty(3 * len(cells), ld)
+        nuniq = ctx.assemble_matched(d_pos, d_quat, d_dim, cls, out, ld, chi=d_chi, n_tgt_local=len(cells),
+                                     tgt_block=tgt_block, tgt_nparts=nparts, tgt_part=part)
+        assert 0 < nuniq <= nuniq_full
+        rows = (3 * cells[:, None] + np.arange(3)[None, :]).reshape(-1)
+        rebuilt[rows] = out[:, :N].cpu().numpy()
+    assert_T_close(rebuilt, dense)
+    assert_T_close(full[:, :N].cpu().numpy(), dense)
+
+
+@pytest.mark.parametrize(("n", "tgt_block"), [(333, 40), (700, 80)])
+def test_lu_dist_factor_once_solve_many(ctx, n, tgt_block):
+    """The two phases of the distributed LU on their own (demag_store on several GPUs keeps the factors)."""
+    N = 3 * n
+    rng = np.random.default_rng(n + 1)
+    Q = rng.normal(size=(N, N))
+    ld = (N + 15) // 16 * 16
+    dQ = torch.zeros(N, ld, dtype=torch.float64, device=ctx.device)
+    dQ[:, :N] = dev(ctx, Q)
+    ipiv = torch.zeros(N, dtype=torch.int32, device=ctx.device)
+    assert ctx.lu_factor_dist(N, N, tgt_block, dQ, ld, ipiv) == 0
+    for seed in range(3):
+        b = np.random.default_rng(seed).normal(size=N)
+        dx = dev(ctx, b)
+        ctx.lu_trisolve_dist(N, N, tgt_block, dQ, ld, ipiv, dx)
+        x = dx.cpu().numpy()
+        resid = np.linalg.norm(Q @ x - b) / (np.linalg.norm(Q) * np.linalg.norm(x))
+        assert resid < 1e-14, resid
+
+
+def test_two_magnets_8000_full_size_vs_oracle(ctx, golden_dir):
+    """The bench workload itself (BASELINE configs[1], N = 24000) against the CPU oracle: 64 sampled rows of
+    the assembled tensor (the rotated chi = 1000 cube's rows included) computed by the oracle here, and the
+    FULL solution against the oracle solve committed in tests/golden/two_magnets_8000_solution.npz
+    (generated by tests/golden/make_two_magnets_8000_solution.py: 66 s of CPU on 8 cores)."""
+    import bench
+
+    w = bench.make_workload("two_magnets_8000")
+    pos, quat, dim = w["pos"], w["quat"], w["dim"]
+    n, N = len(pos), 3 * len(pos)
+    Nmat, ld = _assemble_device(ctx, pos, quat, dim)
+    rng = np.random.default_rng(7)
+    jj = np.sort(np.concatenate([rng.choice(4000, 32, replace=False), 4000 + rng.choice(4000, 32, replace=False)]))
+    H = np.stack([ocf.getBH_cuboid_sources("H", pos[jj], pos, quat, dim,
+                                           R.from_quat(quat).apply(np.tile(np.eye(3)[k], (n, 1)), inverse=True))
+                  for k in range(3)])  # [k, i, jsel, l]
+    ref_rows = ocf.MU0 * H.transpose(2, 3, 1, 0).reshape(len(jj) * 3, N)  # [(jsel,l), (i,k)]
+    rows = (3 * jj[:, None] + np.arange(3)[None, :]).reshape(-1)
+    assert_T_close(Nmat[rows][:, :N].cpu().numpy(), ref_rows)
+    del Nmat
+    gold = np.load(golden_dir / "two_magnets_8000_solution.npz")["x_local"]
+    meta = json.loads((golden_dir / "two_magnets_8000_solution.json").read_text())
+    import hashlib
+
+    assert hashlib.sha256(np.ascontiguousarray(gold).tobytes()).hexdigest() == meta["sha256_x_local"]
+    from magpylib_material_response_b200.demag import apply_demag_arrays
+
+    for solver in ("lu", "gmres"):
+        x = apply_demag_arrays(pos, quat, dim, w["pol"], w["chi"], w["H_ext"], solver=solver, tol=1e-13)
+        err = np.abs(x - gold).max() / np.abs(gold).max()
+        assert err <= J_RTOL, (solver, err)
+    # and through the object API (SoA collection of mesh_Cuboid cells)
+    out = apply_demag(bench.make_collection("two_magnets_8000"))
+    err = np.abs(bench.collection_polarizations(out) - gold).max() / np.abs(gold).max()
+    assert err <= J_RTOL, err

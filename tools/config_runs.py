@@ -27,8 +27,6 @@ if world > 1:
 w = make_workload(name)
 n = len(w["pos"]); N = 3 * n
 kw = dict(pairs_matching=w.get("pairs_matching", False), max_dist=w.get("max_dist", 0), split=w.get("split", 1))
-if world > 1:
-    kw["pairs_matching"] = False  # the multi-GPU path assembles densely (same matrix)
 t0 = time.perf_counter()
 x, info = apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], solver=solver, tol=1e-12,
                              return_info=True, **kw)
