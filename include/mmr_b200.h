@@ -79,12 +79,17 @@ int64_t mmr_ctx_launch_count(mmr_ctx* ctx);
 #define MMR_PROF_MATVEC 5     /* units: matrix bytes streamed                   */
 #define MMR_PROF_PANEL_GEMM 6 /* units: flops of the in-panel rank-W updates    */
 #define MMR_PROF_TRISOLVE 7   /* units: matrix bytes streamed                   */
-#define MMR_PROF_NKINDS 8
+#define MMR_PROF_COMM 8       /* units: bytes broadcast / gathered (NCCL calls)   */
+#define MMR_PROF_NKINDS 9
 int mmr_ctx_set_profiling(mmr_ctx* ctx, int on);
 int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
                     int64_t* launches_out);
 /* Individual record durations (ms) of one class, in launch order; returns the count written. */
 int64_t mmr_ctx_profile_records(mmr_ctx* ctx, int kind, double* ms_out, int64_t cap);
+/* All records in launch order as a timeline: kind (| 0x100 for records of the side stream), start (ms after mmr_ctx_set_profiling(on)) and
+ * duration (ms) -- records of both streams of the context share one device clock.  Returns the count. */
+int64_t mmr_ctx_profile_timeline(mmr_ctx* ctx, int* kind_out, double* start_ms_out, double* dur_ms_out,
+                                 int64_t cap);
 
 /* FP64 roofline denominators of this device, measured now (about 0.1 s): the FMA-pipe peak that bounds
  * the assembly kernel and the tensor-pipe (DMMA.8x8x4) peak that bounds the LU trailing update, in
@@ -153,6 +158,13 @@ int mmr_lu_factor(mmr_ctx* ctx, int64_t N, double* d_Q, int64_t ld, int32_t* d_i
  * overwritten by the solution. */
 int mmr_lu_solve(mmr_ctx* ctx, int64_t N, const double* d_LU, int64_t ld, const int32_t* d_ipiv,
                  double* d_B, int64_t nrhs);
+
+/* The diagonal-block step of a speculative LU panel on its own (exported for tests and micro-benchmarks):
+ * LU WITHOUT interchanges of the nb x nb (nb <= 128) column-major block d_A into d_S (packed L and U, ld lds)
+ * plus the dense inverses of both factors (nb x nb, ld nb).  *rejected_out = 1 when partial pivoting would
+ * have interchanged rows (a multiplier above 1 in magnitude) or a pivot is zero; outputs are then undefined. */
+int mmr_lu_diag_block(mmr_ctx* ctx, const double* d_A, int64_t ld, int nb, double* d_S, int64_t lds,
+                      double* d_Linv, double* d_Uinv, int* rejected_out);
 
 /* C = alpha * op(A) op(B) + beta * C on the FP64 tensor-core (DMMA) path used by the LU
  * trailing update; exported for tests and the roofline measurement.  COLUMN-major (BLAS

@@ -53,6 +53,11 @@ _SIGNATURES = {
         ctypes.c_int64,
         [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int64],
     ),
+    "mmr_ctx_profile_timeline": (
+        ctypes.c_int64,
+        [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+         ctypes.c_int64],
+    ),
     "mmr_fp64_peaks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "mmr_assemble": (
         ctypes.c_int,
@@ -80,6 +85,11 @@ _SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, ctypes.c_void_p, _c_double_p,
          ctypes.c_int64],
+    ),
+    "mmr_lu_diag_block": (
+        ctypes.c_int,
+        [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
+         ctypes.POINTER(ctypes.c_int)],
     ),
     "mmr_dgemm_nn": (
         ctypes.c_int,
@@ -245,7 +255,7 @@ class Context:
     def launch_count(self):
         return int(self.lib.mmr_ctx_launch_count(self.handle))
 
-    PROF_KINDS = ("assemble", "gemm", "panel", "trsm", "laswp", "matvec", "panel_gemm", "trisolve")
+    PROF_KINDS = ("assemble", "gemm", "panel", "trsm", "laswp", "matvec", "panel_gemm", "trisolve", "comm")
 
     def set_profiling(self, on=True):
         _check(self.lib, self.lib.mmr_ctx_set_profiling(self.handle, int(bool(on))))
@@ -259,6 +269,14 @@ class Context:
                                                       ctypes.byref(cnt)))
             out[name] = (ms.value, units.value, cnt.value)
         return out
+
+    def profile_timeline(self, cap=200000):
+        """[(kind name, start ms, duration ms)] of every record since set_profiling(True), launch order."""
+        kinds = (ctypes.c_int * cap)()
+        t0 = (ctypes.c_double * cap)()
+        dt = (ctypes.c_double * cap)()
+        n = self.lib.mmr_ctx_profile_timeline(self.handle, kinds, t0, dt, cap)
+        return [(self.PROF_KINDS[kinds[i] & 0xFF] + ("@side" if kinds[i] & 0x100 else ""), t0[i], dt[i]) for i in range(n)]
 
     def profile_records(self, kind, cap=100000):
         buf = (ctypes.c_double * cap)()
@@ -316,6 +334,13 @@ class Context:
     def lu_solve(self, LU, ld, ipiv, B, nrhs=1):
         _check(self.lib, self.lib.mmr_lu_solve(self.handle, LU.shape[0], _ptr(LU), ld, _ptr(ipiv),
                                                _ptr(B), nrhs))
+
+    def lu_diag_block(self, A, ld, nb, S, lds, Linv, Uinv):
+        """No-pivot LU of the leading nb x nb block + both inverses; returns True if the speculation is rejected."""
+        rej = ctypes.c_int(0)
+        _check(self.lib, self.lib.mmr_lu_diag_block(self.handle, _ptr(A), ld, nb, _ptr(S), lds, _ptr(Linv), _ptr(Uinv),
+                                                    ctypes.byref(rej)))
+        return bool(rej.value)
 
     def dgemm_nn(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
         _check(self.lib, self.lib.mmr_dgemm_nn(self.handle, m, n, k, alpha, _ptr(A), lda, _ptr(B), ldb,

@@ -37,11 +37,13 @@ struct mmr_ctx {
   bool profiling = false;
   struct ProfRec {
     int kind;
+    int side;  // 1: enqueued on the context's side (look-ahead) stream
     cudaEvent_t e0, e1;
     double units;
   };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_base = nullptr;  // recorded by mmr_ctx_set_profiling(on): origin of the timeline
   // side stream + events for look-ahead in the LU
   cudaStream_t side = nullptr;
   bool lookahead = true;

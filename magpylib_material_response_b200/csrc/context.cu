@@ -69,6 +69,7 @@ int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s) {
   if (!ctx->profiling) return -1;
   mmr_ctx::ProfRec r;
   r.kind = kind;
+  r.side = (s == ctx->side) ? 1 : 0;
   r.e0 = prof_event(ctx);
   r.e1 = prof_event(ctx);
   r.units = 0.0;
@@ -93,7 +94,32 @@ extern "C" int mmr_ctx_set_profiling(mmr_ctx* ctx, int on) {
   }
   ctx->prof.clear();
   ctx->profiling = on != 0;
+  if (on) {
+    if (!ctx->prof_base) MMR_CUDA(cudaEventCreate(&ctx->prof_base));
+    MMR_CUDA(cudaEventRecord(ctx->prof_base, ctx->stream));
+  }
   return 0;
+}
+
+extern "C" int64_t mmr_ctx_profile_timeline(mmr_ctx* ctx, int* kind_out, double* start_ms_out, double* dur_ms_out,
+                                            int64_t cap) {
+  if (!ctx || !ctx->prof_base) return 0;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->side) cudaStreamSynchronize(ctx->side);
+  int64_t cnt = 0;
+  for (auto& r : ctx->prof) {
+    if (cnt >= cap) break;
+    float t0 = 0.f, dt = 0.f;
+    if (cudaEventElapsedTime(&t0, ctx->prof_base, r.e0) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&dt, r.e0, r.e1) != cudaSuccess) continue;
+    if (kind_out) kind_out[cnt] = r.kind | (r.side ? 0x100 : 0);
+    if (start_ms_out) start_ms_out[cnt] = t0;
+    if (dur_ms_out) dur_ms_out[cnt] = dt;
+    ++cnt;
+  }
+  cudaGetLastError();
+  return cnt;
 }
 
 extern "C" int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
@@ -180,6 +206,7 @@ extern "C" int mmr_ctx_destroy(mmr_ctx* ctx) {
     cudaEventDestroy(r.e1);
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+  if (ctx->prof_base) cudaEventDestroy(ctx->prof_base);
   if (ctx->laswp_buf) cudaFree(ctx->laswp_buf);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);

@@ -41,6 +41,14 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Speculation guard of the LU ("poison"): `fail` points to a sticky device word that holds kb+1 of the first
+// panel whose speculative (diagonal-pivot) factorization was rejected, or 0.  An operation that needs the
+// result of the panel starting at column `dep` (and hence of all earlier ones) must not write anything once a
+// panel with start <= dep has failed; operations that only depend on earlier panels still run, so the matrix
+// stays in a consistent "everything before the failed panel applied" state the host can resume from.
+__device__ __forceinline__ bool lu_poisoned(int failword, int dep) { return failword != 0 && failword - 1 <= dep; }
+__device__ __forceinline__ int lu_failword(const int* fail) { return fail ? __ldcg(fail) : 0; }
+
 // Sign flip on the integer pipe (a DADD/DMUL negation would compete with the DMMAs for the FP64 pipe).
 __device__ __forceinline__ double flip_sign(double x) {
   return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
@@ -55,10 +63,11 @@ template <bool ALIGNED16, bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                     const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                    int64_t ldc) {
+                    int64_t ldc, const int* __restrict__ fail, int dep) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
+  const int failword = lu_failword(fail);  // consumed before the first store (epilogue)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -174,6 +183,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
   }
   cp_async_wait<0>();
+  if (lu_poisoned(failword, dep)) return;
 
   // epilogue: thread holds rows (lane>>2), cols 2*(lane&3) + {0,1} of each 8x8 fragment
 #pragma unroll
@@ -215,10 +225,11 @@ template <bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_fast_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                          const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                         int64_t ldc, int prefetch_dist) {
+                         int64_t ldc, int prefetch_dist, const int* __restrict__ fail, int dep) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
+  const int failword = lu_failword(fail);  // consumed before the first store (epilogue)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -344,6 +355,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     ls = (ls + 1 == STAGES) ? 0 : ls + 1;
   }
   cp_async_wait<0>();
+  if (lu_poisoned(failword, dep)) return;
 
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
@@ -372,4 +384,4 @@ __global__ void __launch_bounds__(THREADS, 2)
 // host-side launcher (defined in lu.cu)
 int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                     double* C, int64_t ldc);
+                     double* C, int64_t ldc, const int* fail = nullptr, int dep = 0);

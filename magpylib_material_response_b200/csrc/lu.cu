@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "dgemm.cuh"
+#include "panel128.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -796,13 +797,13 @@ __global__ void lu_gather_kernel(const double* __restrict__ v, const int* __rest
 
 int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                     double* C, int64_t ldc) {
+                     double* C, int64_t ldc, const int* fail, int dep) {
   using namespace mmr_gemm;
   if (m <= 0 || n <= 0) return 0;
   const bool aligned = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
   const bool subtract = (alpha == -1.0 && beta == 1.0);
   typedef void (*kern_t)(int, int, int, double, const double*, int64_t, const double*, int64_t, double,
-                         double*, int64_t);
+                         double*, int64_t, const int*, int);
   static const kern_t kerns[4] = {dgemm_nn_kernel<false, false>, dgemm_nn_kernel<false, true>,
                                   dgemm_nn_kernel<true, false>, dgemm_nn_kernel<true, true>};
   const int which = (aligned ? 2 : 0) + (subtract ? 1 : 0);
@@ -826,13 +827,13 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     // L2 prefetch distance for the C tiles: the number of CTAs resident at once (2 per SM)
     const int pf = (prefetch_on && ntiles > 2 * (int64_t)ctx->sm_count) ? 2 * ctx->sm_count : 0;
     if (subtract)
-      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf);
+      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf, fail, dep);
     else
-      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf);
+      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf, fail, dep);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }
-  kerns[which]<<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc);
+  kerns[which]<<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, fail, dep);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -1036,9 +1037,10 @@ __device__ __forceinline__ double fast_rcp(double a) {
 // single owner thread -- measured the same 0.4 us per step with 30x more shared-memory stores.)
 __global__ void __launch_bounds__(512, 1)
     lu_diag_nopiv_tile_kernel(const double* __restrict__ A, int64_t ld, int kb, int nb, double* __restrict__ S,
-                              int64_t lds, int* __restrict__ flag) {
+                              int64_t lds, int* __restrict__ fail) {
   __shared__ double lcol[2][128];
   __shared__ int s_bad;
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), kb - 1)) return;  // an earlier panel was rejected
   const int tid = threadIdx.x, tr = tid & 31, tc = tid >> 5;
   double v[4][8];
 #pragma unroll
@@ -1109,7 +1111,7 @@ __global__ void __launch_bounds__(512, 1)
   }
   if (bad) s_bad = 1;
   __syncthreads();
-  if (tid == 0) *flag = s_bad;
+  if (tid == 0 && s_bad) atomicCAS(fail, 0, kb + 1);  // sticky: the first rejected panel
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1126,8 +1128,9 @@ __global__ void __launch_bounds__(512, 1)
 constexpr int TINV_COLS = 32;
 __global__ void __launch_bounds__(256)
     lu_tri_inv_kernel(const double* __restrict__ S, int64_t lds, int nb, double* __restrict__ Linv,
-                      double* __restrict__ Uinv) {
+                      double* __restrict__ Uinv, const int* __restrict__ fail, int dep) {
   extern __shared__ __align__(16) double sm[];
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), dep)) return;
   double* Bs = sm;                          // [TINV_COLS][nb+1]
   double* Ls = sm + TINV_COLS * (nb + 1);   // Ls[c*(nb+1) + r], r >= c
   const bool upper = blockIdx.y == 1;
@@ -1226,9 +1229,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// flag |= any |S[r, c]| > 1 (or NaN) for r in [r0, m), c in [0, nb)
+// *fail = kb + 1 (if still 0) when any |S[r, c]| > 1 (or NaN) for r in [r0, m), c in [0, nb)
 __global__ void __launch_bounds__(256)
-    lu_spec_check_kernel(const double* __restrict__ S, int64_t lds, int r0, int m, int nb, int* __restrict__ flag) {
+    lu_spec_check_kernel(const double* __restrict__ S, int64_t lds, int r0, int m, int nb, int* __restrict__ fail, int kb) {
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), kb)) return;
   const int64_t rows = m - r0;
   const int64_t total = rows * nb;
   bool bad = false;
@@ -1236,14 +1240,14 @@ __global__ void __launch_bounds__(256)
     const int64_t r = e % rows, c = e / rows;
     bad |= !(fabs(S[c * lds + r0 + r]) <= 1.0);
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(fail, 0, kb + 1);
 }
 
-// if (*flag == 0): A[kb + r, kb + c] = S[r, c] for r < m, c < nb; ipiv[kb + c] = kb + c
+// unless this or an earlier panel was rejected: A[kb + r, kb + c] = S[r, c] for r < m, c < nb; ipiv[kb + c] = kb + c
 __global__ void __launch_bounds__(256)
     lu_spec_commit_kernel(const double* __restrict__ S, int64_t lds, int m, int nb, double* __restrict__ A,
-                          int64_t ld, int kb, int* __restrict__ ipiv, const int* __restrict__ flag) {
-  if (*flag != 0) return;
+                          int64_t ld, int kb, int* __restrict__ ipiv, const int* __restrict__ fail) {
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), kb)) return;
   const int64_t total = (int64_t)m * nb;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e % m, c = e / m;
@@ -1254,14 +1258,16 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
-size_t mmr_lu_spec_scratch_bytes() { return sizeof(double) * NB * NB + 256; }  // U11^-1 + flag
+size_t mmr_lu_spec_scratch_bytes() { return sizeof(double) * NB * NB + 256; }  // U11^-1
 
-// Speculative factorization of the panel columns [kb, kb+nb), rows [kb, N) of A (see above).
-// S: m x nb packed panel buffer (ld = m = N - kb), left filled with the factored panel on success.
-// d_spec: mmr_lu_spec_scratch_bytes() of device scratch.  *ok_out = 1: A, ipiv, Linv and S hold the
-// result; 0: nothing was modified (the caller runs the pivoting path).  Synchronises `strm`.
+// Speculative factorization of the panel columns [kb, kb+nb), rows [kb, N) of A (see above), entirely
+// stream-ordered: no host synchronization.  S: m x nb packed panel buffer (ld = m = N - kb).  d_fail: the
+// sticky device word of this factorization.  If the panel passes, A, ipiv, Linv and S hold its result; if it
+// (or an earlier one) is rejected, *d_fail = (start of the first rejected panel) + 1, nothing of this panel is
+// written, and every later operation that depends on it skips its stores (lu_poisoned) -- the host finds out
+// when it reads *d_fail at the end and resumes from that panel with the pivoting kernels.
 int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
-                      double* S, double* Linv, void* d_spec, int* ok_out) {
+                      double* S, double* Linv, void* d_spec, int* d_fail) {
   const size_t inv_smem = ((size_t)TINV_COLS * (NB + 1) + (size_t)NB * (NB + 1)) * sizeof(double);
   {
     const int rc0 = mmr_func_smem(ctx, (const void*)lu_tri_inv_kernel, inv_smem);
@@ -1269,33 +1275,68 @@ int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, in
   }
   const int m = N - kb;
   double* Uinv = (double*)d_spec;
-  int* d_flag = (int*)((char*)d_spec + sizeof(double) * NB * NB);
+  static int panel_v1 = -1;
+  if (panel_v1 < 0) {
+    const char* e = getenv("MMR_LU_PANEL_V1");  // 1: the round-1 kernel pair (one-CTA LU + 8-CTA inverses)
+    panel_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
   const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, strm);
-  lu_diag_nopiv_tile_kernel<<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_flag);
-  MMR_CHECK_LAUNCH(ctx);
-  const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
-  lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, strm>>>(S, m, nb, Linv, Uinv);
-  MMR_CHECK_LAUNCH(ctx);
+  if (panel_v1) {
+    lu_diag_nopiv_tile_kernel<<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_fail);
+    MMR_CHECK_LAUNCH(ctx);
+    const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
+    lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, strm>>>(S, m, nb, Linv, Uinv, d_fail, kb);
+    MMR_CHECK_LAUNCH(ctx);
+  } else {
+    // one cluster launch: blocked no-pivot LU of the diagonal block + both triangular inverses (panel128.cuh)
+    const int rc1 = mmr_func_smem(ctx, (const void*)mmr_panel::lu_diag_inv_cluster_kernel, mmr_panel::PANEL_SMEM);
+    if (rc1) return rc1;
+    mmr_panel::lu_diag_inv_cluster_kernel<<<mmr_panel::PCLUSTER, mmr_panel::PTHREADS, mmr_panel::PANEL_SMEM, strm>>>(
+        A, ld, kb, nb, S, m, Linv, Uinv, d_fail);
+    MMR_CHECK_LAUNCH(ctx);
+  }
   mmr_prof_end(ctx, pidx, (double)nb, strm);
   if (m > nb) {
     const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
     int rc = mmr_dgemm_launch(ctx, strm, m - nb, nb, nb, 1.0, A + (int64_t)kb * ld + kb + nb, ld, Uinv, nb, 0.0,
-                              S + nb, m);
+                              S + nb, m, d_fail, kb);
     if (rc) return rc;
     mmr_prof_end(ctx, pg, 2.0 * (m - nb) * (double)nb * nb, strm);
     const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)(m - nb) * nb, 256 * 8));
-    lu_spec_check_kernel<<<g, 256, 0, strm>>>(S, m, nb, m, nb, d_flag);
+    lu_spec_check_kernel<<<g, 256, 0, strm>>>(S, m, nb, m, nb, d_fail, kb);
     MMR_CHECK_LAUNCH(ctx);
   }
   {
     const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)m * nb, 256 * 8));
-    lu_spec_commit_kernel<<<g, 256, 0, strm>>>(S, m, m, nb, A, ld, kb, d_ipiv, d_flag);
+    lu_spec_commit_kernel<<<g, 256, 0, strm>>>(S, m, m, nb, A, ld, kb, d_ipiv, d_fail);
     MMR_CHECK_LAUNCH(ctx);
   }
-  int* h_flag = (int*)((char*)ctx->hpin + 128);
-  MMR_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, strm));
-  MMR_CUDA(cudaStreamSynchronize(strm));
-  *ok_out = (*h_flag == 0) ? 1 : 0;
+  return 0;
+}
+
+// The diagonal-block step of the speculative panel on its own (tests / micro-benchmarks): no-pivot LU of the
+// nb x nb (<= 128) leading block of column-major d_A into d_S (ld lds, packed L and U), L^-1 and U^-1 (dense
+// nb x nb, ld nb).  *rejected_out = 1 if the speculation check fails (zero pivot or a multiplier above 1).
+extern "C" int mmr_lu_diag_block(mmr_ctx* ctx, const double* d_A, int64_t ld, int nb, double* d_S, int64_t lds,
+                                 double* d_Linv, double* d_Uinv, int* rejected_out) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(nb >= 1 && nb <= NB && ld >= nb && lds >= nb, "bad block size / leading dimension");
+  MMR_ARG(d_A && d_S && d_Linv && d_Uinv, "NULL pointer");
+  DeviceGuard g(ctx->device);
+  int rc = mmr_ws_reserve(ctx, 256);
+  if (rc) return rc;
+  rc = mmr_hpin_reserve(ctx, 256);
+  if (rc) return rc;
+  int* d_fail = (int*)ctx->ws;
+  MMR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
+  rc = mmr_func_smem(ctx, (const void*)mmr_panel::lu_diag_inv_cluster_kernel, mmr_panel::PANEL_SMEM);
+  if (rc) return rc;
+  mmr_panel::lu_diag_inv_cluster_kernel<<<mmr_panel::PCLUSTER, mmr_panel::PTHREADS, mmr_panel::PANEL_SMEM, ctx->stream>>>(
+      d_A, ld, 0, nb, d_S, lds, d_Linv, d_Uinv, d_fail);
+  MMR_CHECK_LAUNCH(ctx);
+  MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (rejected_out) *rejected_out = (*(int*)ctx->hpin != 0) ? 1 : 0;
   return 0;
 }
 
@@ -1317,8 +1358,10 @@ struct LaswpPerm {
 };
 
 __global__ void __launch_bounds__(32)
-    lu_laswp_prepare_kernel(const int* __restrict__ ipiv, int k0, int nb, LaswpPerm* __restrict__ out) {
+    lu_laswp_prepare_kernel(const int* __restrict__ ipiv, int k0, int nb, LaswpPerm* __restrict__ out,
+                            const int* __restrict__ fail) {
   __shared__ int piv[NB], rows[LASWP_MAX], cur[LASWP_MAX];
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), k0)) return;  // the panel [k0, k0+nb) was never committed
   const int lane = threadIdx.x;
   int any = 0;
   for (int i = lane; i < nb; i += 32) {
@@ -1384,7 +1427,9 @@ __global__ void __launch_bounds__(32)
 // one warp per column gathers the moved rows into registers and scatters them.
 __global__ void __launch_bounds__(256)
     lu_laswp_apply_kernel(double* __restrict__ A, int64_t ld, int col_begin, int col_end,
-                          const LaswpPerm* __restrict__ p0, const LaswpPerm* __restrict__ p1) {
+                          const LaswpPerm* __restrict__ p0, const LaswpPerm* __restrict__ p1,
+                          const int* __restrict__ fail, int dep) {
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), dep)) return;
   const int m0 = p0->moved, m1 = p1 ? p1->moved : 0;
   if ((m0 | m1) == 0) return;
   __shared__ int s_rows[LASWP_MAX], s_src[LASWP_MAX];
@@ -1429,25 +1474,26 @@ static int laswp_slots(mmr_ctx* ctx, LaswpPerm** out) {
 }
 
 // Turns the interchanges ipiv[k0..k1) into the permutation record `slot` (0..5).
-int mmr_lu_laswp_prepare(mmr_ctx* ctx, cudaStream_t strm, const int* d_ipiv, int k0, int k1, int slot) {
+int mmr_lu_laswp_prepare(mmr_ctx* ctx, cudaStream_t strm, const int* d_ipiv, int k0, int k1, int slot,
+                         const int* d_fail = nullptr) {
   LaswpPerm* perms;
   int rc = laswp_slots(ctx, &perms);
   if (rc) return rc;
-  lu_laswp_prepare_kernel<<<1, 32, 0, strm>>>(d_ipiv, k0, k1 - k0, perms + slot);
+  lu_laswp_prepare_kernel<<<1, 32, 0, strm>>>(d_ipiv, k0, k1 - k0, perms + slot, d_fail);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
 
 // Applies record slot0 and then (slot1 >= 0) slot1 to the local columns [col_begin, col_end).
 int mmr_lu_laswp_apply(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int col_begin, int col_end, int slot0,
-                       int slot1) {
+                       int slot1, const int* d_fail = nullptr, int dep = 0) {
   if (col_end <= col_begin) return 0;
   LaswpPerm* perms;
   int rc = laswp_slots(ctx, &perms);
   if (rc) return rc;
   const int warps = 8;
   lu_laswp_apply_kernel<<<(unsigned)ceil_div64(col_end - col_begin, warps), warps * 32, 0, strm>>>(
-      A, ld, col_begin, col_end, perms + slot0, slot1 >= 0 ? perms + slot1 : nullptr);
+      A, ld, col_begin, col_end, perms + slot0, slot1 >= 0 ? perms + slot1 : nullptr, d_fail, dep);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -1455,12 +1501,12 @@ int mmr_lu_laswp_apply(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, i
 // Applies the interchanges ipiv[k0..k1) to local columns [col_begin, col_end) (prepare + apply;
 // one scratch record per stream: calls on one stream are ordered).
 int mmr_lu_laswp(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int k0, int k1, int col_begin, int col_end,
-                 const int* d_ipiv) {
+                 const int* d_ipiv, const int* d_fail = nullptr) {
   if (col_end <= col_begin || k1 <= k0) return 0;
   const int slot = (strm == ctx->stream) ? 0 : 1;
-  int rc = mmr_lu_laswp_prepare(ctx, strm, d_ipiv, k0, k1, slot);
+  int rc = mmr_lu_laswp_prepare(ctx, strm, d_ipiv, k0, k1, slot, d_fail);
   if (rc) return rc;
-  return mmr_lu_laswp_apply(ctx, strm, A, ld, col_begin, col_end, slot, -1);
+  return mmr_lu_laswp_apply(ctx, strm, A, ld, col_begin, col_end, slot, -1, d_fail, k0);
 }
 
 int mmr_lu_trsm(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, int nb, double* B, int64_t ldb, int ncols) {
@@ -1517,7 +1563,7 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
     const char* e = getenv("MMR_LU_SPEC");  // 0: always the pivoting strip kernels
     spec_default = (e && e[0] == '0') ? 0 : 1;
   }
-  bool spec_on = spec_default != 0;  // switched off for the rest of this factorization after a failed check
+  bool spec_on = spec_default != 0;  // switched off for the rest of this factorization after a rejected panel
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
   const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
   const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256 * 256) : 0;
@@ -1525,121 +1571,138 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 256);
   if (rc) return rc;
-  int* d_info = (int*)ctx->ws;
+  int* d_info = (int*)ctx->ws;  // [0] zero-pivot report, [1] speculation guard (lu_poisoned)
+  int* d_fail = d_info + 1;
   void* scratch = (char*)ctx->ws + 256;
   double* Lbuf = (double*)((char*)ctx->ws + 256 + scratch_bytes);
   void* d_spec = (char*)Lbuf + 4 * sizeof(double) * NB * NB;
   double* Sbuf = (double*)((char*)d_spec + spec_bytes);
   // inverse of the unit-lower diagonal block of inner panel `inner` of the outer block at kb
   auto Linv = [&](int kb, int inner) { return Lbuf + (size_t)((((kb / OB) & 1) << 1) + inner) * NB * NB; };
-  MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+  MMR_CUDA(cudaMemsetAsync(d_info, 0, 2 * sizeof(int), ctx->stream));
   double* A = d_Q;
   cudaStream_t main_s = ctx->stream;
   cudaStream_t side_s = ctx->side;
+  // start of the last panel of the outer block at kb: what a consumer of the whole block depends on
+  auto last_panel = [&](int kb) { return (min(OB, N - kb) > NB) ? kb + NB : kb; };
   // interchange records: slot(kb, inner), prepared once per panel on the stream that factored it
   auto pslot = [&](int kb, int inner) { return 2 + ((((kb / OB) & 1) << 1) + inner); };
-  auto laswp = [&](cudaStream_t s, int cb, int ce, int slot0, int slot1) -> int {
+  auto laswp = [&](cudaStream_t s, int cb, int ce, int slot0, int slot1, int dep) -> int {
     if (ce <= cb) return 0;
     const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, s);
-    const int r = mmr_lu_laswp_apply(ctx, s, A, ld, cb, ce, slot0, slot1);
+    const int r = mmr_lu_laswp_apply(ctx, s, A, ld, cb, ce, slot0, slot1, d_fail, dep);
     mmr_prof_end(ctx, ps, 32.0 * NB * (double)(ce - cb), s);
     return r;
   };
   // B <- Linv * B in place on rows [r0, r0+nb) of columns [cb, ce): one m-tile, so each CTA has its
   // whole B tile in shared memory before it stores and no other CTA touches those columns.
-  auto trsm = [&](cudaStream_t s, const double* Li, int r0, int nb, int cb, int ce) -> int {
+  auto trsm = [&](cudaStream_t s, const double* Li, int r0, int nb, int cb, int ce, int dep) -> int {
     const int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, s);
     const int r = mmr_dgemm_launch(ctx, s, nb, ce - cb, nb, 1.0, Li, nb, A + (int64_t)cb * ld + r0, ld, 0.0,
-                                   A + (int64_t)cb * ld + r0, ld);
+                                   A + (int64_t)cb * ld + r0, ld, d_fail, dep);
     mmr_prof_end(ctx, ps, 2.0 * nb * nb * (double)(ce - cb), s);
     return r;
   };
   // A[r0:r1, cb:ce] -= A[r0:r1, k0:k0+k] * A[k0:k0+k, cb:ce]
-  auto gemm = [&](cudaStream_t s, int kind, int r0, int r1, int k0, int k, int cb, int ce) -> int {
+  auto gemm = [&](cudaStream_t s, int kind, int r0, int r1, int k0, int k, int cb, int ce, int dep) -> int {
     if (r1 <= r0 || ce <= cb) return 0;
     const int ps = mmr_prof_begin(ctx, kind, s);
     const int r = mmr_dgemm_launch(ctx, s, r1 - r0, ce - cb, k, -1.0, A + (int64_t)k0 * ld + r0, ld,
-                                   A + (int64_t)cb * ld + k0, ld, 1.0, A + (int64_t)cb * ld + r0, ld);
+                                   A + (int64_t)cb * ld + k0, ld, 1.0, A + (int64_t)cb * ld + r0, ld, d_fail, dep);
     mmr_prof_end(ctx, ps, 2.0 * (r1 - r0) * (double)(ce - cb) * k, s);
     return r;
   };
-  // panel [kb, kb+nb) and the inverse of its unit-lower diagonal block: speculative (diagonal
-  // pivots, verified; blocks the host until the check is known) or the pivoting strip kernels
+  // panel [kb, kb+nb) and the inverse of its unit-lower diagonal block: speculative (diagonal pivots,
+  // verified on the device, stream-ordered) or the pivoting strip kernels
   auto panel = [&](cudaStream_t s, int kb, int nb, double* Linv_out) -> int {
-    if (spec_on) {
-      int ok = 0;
-      const int r = mmr_lu_panel_spec(ctx, s, A, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, &ok);
-      if (r || ok) return r;
-      spec_on = false;
-    }
+    if (spec_on) return mmr_lu_panel_spec(ctx, s, A, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, d_fail);
     const int r = mmr_lu_panel(ctx, s, A, ld, N, kb, nb, d_ipiv, d_info, scratch);
     if (r) return r;
     return mmr_lu_trtri(ctx, s, A + (int64_t)kb * ld + kb, ld, nb, Linv_out);
   };
   // factor the outer block [kb, kb+ob): panel 0, its update of panel 1's columns, panel 1
-  auto factor_outer = [&](cudaStream_t s, int kb, int ob) -> int {
+  // (first_inner = 1: panel 0 and its update of panel 1's columns are already done -- resuming after a
+  // rejected panel 1)
+  auto factor_outer = [&](cudaStream_t s, int kb, int ob, int first_inner) -> int {
     const int nb0 = min(NB, ob);
-    int r = panel(s, kb, nb0, Linv(kb, 0));
-    if (r) return r;
-    r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, kb, kb + nb0, pslot(kb, 0));
-    if (r || ob <= NB) return r;
+    int r = 0;
+    if (first_inner == 0) {
+      if ((r = panel(s, kb, nb0, Linv(kb, 0)))) return r;
+      if ((r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, kb, kb + nb0, pslot(kb, 0), d_fail))) return r;
+    }
+    if (ob <= NB) return 0;
     const int k1 = kb + NB, nb1 = ob - NB;
-    if ((r = laswp(s, k1, k1 + nb1, pslot(kb, 0), -1))) return r;
-    if ((r = trsm(s, Linv(kb, 0), kb, NB, k1, k1 + nb1))) return r;
-    if ((r = gemm(s, MMR_PROF_PANEL_GEMM, k1, N, kb, NB, k1, k1 + nb1))) return r;
+    if (first_inner == 0) {
+      if ((r = laswp(s, k1, k1 + nb1, pslot(kb, 0), -1, kb))) return r;
+      if ((r = trsm(s, Linv(kb, 0), kb, NB, k1, k1 + nb1, kb))) return r;
+      if ((r = gemm(s, MMR_PROF_PANEL_GEMM, k1, N, kb, NB, k1, k1 + nb1, kb))) return r;
+    }
     if ((r = panel(s, k1, nb1, Linv(kb, 1)))) return r;
-    if ((r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, k1, k1 + nb1, pslot(kb, 1)))) return r;
-    return laswp(s, kb, k1, pslot(kb, 1), -1);  // panel 1's interchanges on panel 0's columns
+    if ((r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, k1, k1 + nb1, pslot(kb, 1), d_fail))) return r;
+    return laswp(s, kb, k1, pslot(kb, 1), -1, k1);  // panel 1's interchanges on panel 0's columns
   };
   // trailing update of the column range [cb, ce) by the outer block [kb, kb+ob)
   auto update_cols = [&](int kb, int ob, int cb, int ce) -> int {
     if (ce <= cb) return 0;
     const int nb0 = min(NB, ob), nb1 = ob - nb0;
-    int r = laswp(main_s, cb, ce, pslot(kb, 0), nb1 > 0 ? pslot(kb, 1) : -1);
+    const int dep = last_panel(kb);
+    int r = laswp(main_s, cb, ce, pslot(kb, 0), nb1 > 0 ? pslot(kb, 1) : -1, dep);
     if (r) return r;
-    if ((r = trsm(main_s, Linv(kb, 0), kb, nb0, cb, ce))) return r;
+    if ((r = trsm(main_s, Linv(kb, 0), kb, nb0, cb, ce, dep))) return r;
     if (nb1 > 0) {
-      if ((r = gemm(main_s, MMR_PROF_TRSM, kb + nb0, kb + ob, kb, nb0, cb, ce))) return r;
-      if ((r = trsm(main_s, Linv(kb, 1), kb + nb0, nb1, cb, ce))) return r;
+      if ((r = gemm(main_s, MMR_PROF_TRSM, kb + nb0, kb + ob, kb, nb0, cb, ce, dep))) return r;
+      if ((r = trsm(main_s, Linv(kb, 1), kb + nb0, nb1, cb, ce, dep))) return r;
     }
-    return gemm(main_s, MMR_PROF_GEMM, kb + ob, N, kb, ob, cb, ce);
+    return gemm(main_s, MMR_PROF_GEMM, kb + ob, N, kb, ob, cb, ce, dep);
   };
   // Look-ahead (depth 1): as soon as the columns of outer block k+1 have received the update of
   // block k, block k+1 is factored on the high-priority side stream while the main stream applies
   // the rest of update k.  The two touch disjoint column ranges.
   const bool lookahead = ctx->lookahead;
-  rc = factor_outer(main_s, 0, min(OB, N));
-  if (rc) return rc;
-  for (int kb = 0; kb < N; kb += OB) {
-    const int ob = min(OB, N - kb);
-    const int next = kb + ob;
-    // interchanges of this outer block on the columns already factored
-    if ((rc = laswp(main_s, 0, kb, pslot(kb, 0), ob > NB ? pslot(kb, 1) : -1))) return rc;
-    if (next >= N) break;
-    const int ob2 = min(OB, N - next);
-    rc = update_cols(kb, ob, next, next + ob2);
-    if (rc) return rc;
-    if (lookahead) {
-      // the main stream's work is enqueued first: the speculative panels make the host wait for
-      // the side stream, and the device must not run out of queued work meanwhile
-      MMR_CUDA(cudaEventRecord(ctx->ev[0], main_s));
-      rc = update_cols(kb, ob, next + ob2, N);
-      if (rc) return rc;
-      MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
-      rc = factor_outer(side_s, next, ob2);
-      if (rc) return rc;
-      MMR_CUDA(cudaEventRecord(ctx->ev[1], side_s));
-      MMR_CUDA(cudaStreamWaitEvent(main_s, ctx->ev[1], 0));
-    } else {
-      rc = update_cols(kb, ob, next + ob2, N);
-      if (rc) return rc;
-      rc = factor_outer(main_s, next, ob2);
-      if (rc) return rc;
+  // One pass over the outer blocks from kb0 on.  Entry state: everything left of kb0 is factored and applied,
+  // block kb0 has received all earlier updates (and, with first_inner = 1, its panel 0 is done).
+  auto run = [&](int kb0, int first_inner) -> int {
+    int r = factor_outer(main_s, kb0, min(OB, N - kb0), first_inner);
+    if (r) return r;
+    for (int kb = kb0; kb < N; kb += OB) {
+      const int ob = min(OB, N - kb);
+      const int next = kb + ob;
+      // interchanges of this outer block on the columns already factored
+      if ((r = laswp(main_s, 0, kb, pslot(kb, 0), ob > NB ? pslot(kb, 1) : -1, last_panel(kb)))) return r;
+      if (next >= N) break;
+      const int ob2 = min(OB, N - next);
+      if ((r = update_cols(kb, ob, next, next + ob2))) return r;
+      if (lookahead) {
+        MMR_CUDA(cudaEventRecord(ctx->ev[0], main_s));
+        if ((r = update_cols(kb, ob, next + ob2, N))) return r;
+        MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
+        if ((r = factor_outer(side_s, next, ob2, 0))) return r;
+        MMR_CUDA(cudaEventRecord(ctx->ev[1], side_s));
+        MMR_CUDA(cudaStreamWaitEvent(main_s, ctx->ev[1], 0));
+      } else {
+        if ((r = update_cols(kb, ob, next + ob2, N))) return r;
+        if ((r = factor_outer(main_s, next, ob2, 0))) return r;
+      }
     }
+    return 0;
+  };
+  int* h_info = (int*)ctx->hpin;
+  int kb0 = 0, first_inner = 0;
+  for (;;) {
+    rc = run(kb0, first_inner);
+    if (rc) return rc;
+    MMR_CUDA(cudaMemcpyAsync(h_info, d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!spec_on || h_info[1] == 0) break;
+    // a speculative panel was rejected at column kf: everything that depends on it skipped its stores, so the
+    // matrix is exactly in the entry state of run() for that block -- resume there with the pivoting kernels
+    const int kf = h_info[1] - 1;
+    spec_on = false;
+    kb0 = kf / OB * OB;
+    first_inner = (kf > kb0) ? 1 : 0;
+    MMR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
   }
-  MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  MMR_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (info_out) *info_out = *(int*)ctx->hpin;
+  if (info_out) *info_out = h_info[0];
   return 0;
 }
 
@@ -1735,6 +1798,12 @@ extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64
 
 namespace {
 
+// fold the guard word that arrived with a broadcast record into this rank's sticky guard
+__global__ void lu_absorb_fail_kernel(const int* __restrict__ rec_fail, int* __restrict__ fail) {
+  const int f = *rec_fail;
+  if (f != 0) atomicCAS(fail, 0, f);
+}
+
 // b[c0 + c] -= sum_{r in [r0, r1)} Acol[(c0 + c)*ld + r] * x[r]; one CTA per column
 __global__ void __launch_bounds__(256)
     lu_gemv_t_block_kernel(const double* __restrict__ Acol, int64_t ld, int r0, int r1, int c0,
@@ -1815,11 +1884,11 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
   bool spec_on = spec_default != 0;
 
   // workspace: [info | strip scratch | spec scratch | 2 x broadcast record | spec panel]
-  // broadcast record of an outer block: header (L11^-1 of both panels, the block's pivots) + packed
-  // panel (m x ob, ld = m): ONE ncclBroadcast per outer block.
+  // broadcast record of an outer block: header (L11^-1 of both panels, the block's pivots, the owner's
+  // speculation guard word) + packed panel (m x ob, ld = m): ONE ncclBroadcast per outer block.
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
   const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
-  const size_t hdr_doubles = 2 * (size_t)NB * NB + NB;  // + 2*NB ints
+  const size_t hdr_doubles = 2 * (size_t)NB * NB + NB + 2;  // 2 x L11^-1, 2*NB pivot ints, guard word (+ pad)
   const size_t rec_bytes = ((sizeof(double) * (hdr_doubles + (size_t)N * obw) + 255) / 256) * 256;
   const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256) * 256 : 0;
   int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + spec_bytes + 2 * rec_bytes + sbuf_bytes + 512);
@@ -1827,7 +1896,8 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
   rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
   if (rc) return rc;
   char* base = (char*)ctx->ws;
-  int* d_info = (int*)base;
+  int* d_info = (int*)base;  // [0] zero-pivot report, [1] speculation guard (lu_poisoned)
+  int* d_fail = d_info + 1;
   void* scratch = base + 256;
   void* d_spec = base + 256 + scratch_bytes;
   int* d_ipiv = d_ipiv_out;
@@ -1836,53 +1906,59 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
   double* Sbuf = (double*)(base + 256 + scratch_bytes + spec_bytes + 2 * rec_bytes);
   auto LinvOf = [&](int s, int inner) { return rec[s & 1] + (size_t)inner * NB * NB; };
   auto IpivOf = [&](int s) { return (int*)(rec[s & 1] + 2 * (size_t)NB * NB); };
+  auto FailOf = [&](int s) { return (int*)(rec[s & 1] + 2 * (size_t)NB * NB + NB); };
   auto PanelOf = [&](int s) { return rec[s & 1] + hdr_doubles; };
   auto pslot = [&](int s, int inner) { return 2 + (((s & 1) << 1) + inner); };
-  MMR_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
-  MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
-  MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));  // the side stream starts after everything queued so far
+  // start of the last panel of block s: what a consumer of the whole block depends on
+  auto last_panel = [&](int s) { return (min(obw, N - s * obw) > NB) ? s * obw + NB : s * obw; };
+  MMR_CUDA(cudaMemsetAsync(d_info, 0, 2 * sizeof(int), st));
   double* Al = d_Qlocal;
 
-  auto trsm = [&](cudaStream_t s_, const double* Li, int nb, double* Bp, int ncols) -> int {
+  auto trsm = [&](cudaStream_t s_, const double* Li, int nb, double* Bp, int ncols, int dep) -> int {
     const int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, s_);
-    const int r = mmr_dgemm_launch(ctx, s_, nb, ncols, nb, 1.0, Li, nb, Bp, ld, 0.0, Bp, ld);
+    const int r = mmr_dgemm_launch(ctx, s_, nb, ncols, nb, 1.0, Li, nb, Bp, ld, 0.0, Bp, ld, d_fail, dep);
     mmr_prof_end(ctx, ps, 2.0 * nb * nb * (double)ncols, s_);
     return r;
   };
   // panel of the owner's local storage `Ash` (global column c at Ash + c*ld) and its L11^-1
   auto panel = [&](cudaStream_t s_, double* Ash, int kb, int nb, double* Linv_out) -> int {
-    if (spec_on) {
-      int ok = 0;
-      const int r = mmr_lu_panel_spec(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, &ok);
-      if (r || ok) return r;
-      spec_on = false;
-    }
+    if (spec_on) return mmr_lu_panel_spec(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, d_fail);
     const int r = mmr_lu_panel(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
     if (r) return r;
     return mmr_lu_trtri(ctx, s_, Ash + (int64_t)kb * ld + kb, ld, nb, Linv_out);
   };
   // factor outer block s (owned by this rank) on stream `strm` and fill its broadcast record
-  auto factor_and_pack = [&](int s, cudaStream_t strm) -> int {
+  // (first_inner = 1: resuming after a rejected panel 1 -- panel 0 is committed in A, its L11^-1 is rebuilt)
+  auto factor_and_pack = [&](int s, cudaStream_t strm, int first_inner) -> int {
     const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
     const int nb0 = min(NB, ob), nb1 = ob - nb0;
     double* Ash = Al + ((int64_t)(s / R) * obw - kb) * ld;  // global column kb -> my local column
-    int r = panel(strm, Ash, kb, nb0, LinvOf(s, 0));
-    if (r) return r;
+    int r = 0;
+    if (first_inner == 0) {
+      if ((r = panel(strm, Ash, kb, nb0, LinvOf(s, 0)))) return r;
+    } else if ((r = mmr_lu_trtri(ctx, strm, Ash + (int64_t)kb * ld + kb, ld, nb0, LinvOf(s, 0)))) {
+      return r;
+    }
     if (nb1 > 0) {
       const int k1 = kb + nb0;
-      if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, kb, k1, k1, k1 + nb1, d_ipiv))) return r;
-      if ((r = trsm(strm, LinvOf(s, 0), nb0, Ash + (int64_t)k1 * ld + kb, nb1))) return r;
-      const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
-      r = mmr_dgemm_launch(ctx, strm, N - k1, nb1, nb0, -1.0, Ash + (int64_t)kb * ld + k1, ld,
-                           Ash + (int64_t)k1 * ld + kb, ld, 1.0, Ash + (int64_t)k1 * ld + k1, ld);
-      if (r) return r;
-      mmr_prof_end(ctx, pg, 2.0 * (N - k1) * (double)nb1 * nb0, strm);
+      if (first_inner == 0) {
+        if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, kb, k1, k1, k1 + nb1, d_ipiv, d_fail))) return r;
+        if ((r = trsm(strm, LinvOf(s, 0), nb0, Ash + (int64_t)k1 * ld + kb, nb1, kb))) return r;
+        const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
+        r = mmr_dgemm_launch(ctx, strm, N - k1, nb1, nb0, -1.0, Ash + (int64_t)kb * ld + k1, ld,
+                             Ash + (int64_t)k1 * ld + kb, ld, 1.0, Ash + (int64_t)k1 * ld + k1, ld, d_fail, kb);
+        if (r) return r;
+        mmr_prof_end(ctx, pg, 2.0 * (N - k1) * (double)nb1 * nb0, strm);
+      }
       if ((r = panel(strm, Ash, k1, nb1, LinvOf(s, 1)))) return r;
-      if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, k1, k1 + nb1, kb, k1, d_ipiv))) return r;
+      if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, k1, k1 + nb1, kb, k1, d_ipiv, d_fail))) return r;
     }
+    // (unconditional copies: after a rejected panel the record is garbage, but it carries the guard word and
+    // every consumer of it skips its stores)
     MMR_CUDA(cudaMemcpy2DAsync(PanelOf(s), sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
                                sizeof(double) * m, ob, cudaMemcpyDeviceToDevice, strm));
     MMR_CUDA(cudaMemcpyAsync(IpivOf(s), d_ipiv + kb, sizeof(int) * ob, cudaMemcpyDeviceToDevice, strm));
+    MMR_CUDA(cudaMemcpyAsync(FailOf(s), d_fail, sizeof(int), cudaMemcpyDeviceToDevice, strm));
     return 0;
   };
   // apply outer block s (interchanges, U12 in two 128-row steps, one rank-ob update) to my local
@@ -1891,103 +1967,116 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
     if (c1 <= c0) return 0;
     const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
     const int nb0 = min(NB, ob), nb1 = ob - nb0;
+    const int dep = last_panel(s);
     const double* P = PanelOf(s);
     double* B = Al + (int64_t)c0 * ld + kb;
     int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
-    int r = mmr_lu_laswp_apply(ctx, st, Al, ld, c0, c1, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1);
+    int r = mmr_lu_laswp_apply(ctx, st, Al, ld, c0, c1, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1, d_fail, dep);
     if (r) return r;
     mmr_prof_end(ctx, ps, 32.0 * ob * (double)(c1 - c0), st);
-    if ((r = trsm(st, LinvOf(s, 0), nb0, B, c1 - c0))) return r;
+    if ((r = trsm(st, LinvOf(s, 0), nb0, B, c1 - c0, dep))) return r;
     if (nb1 > 0) {
       ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
-      r = mmr_dgemm_launch(ctx, st, nb1, c1 - c0, nb0, -1.0, P + nb0, m, B, ld, 1.0, B + nb0, ld);
+      r = mmr_dgemm_launch(ctx, st, nb1, c1 - c0, nb0, -1.0, P + nb0, m, B, ld, 1.0, B + nb0, ld, d_fail, dep);
       if (r) return r;
       mmr_prof_end(ctx, ps, 2.0 * nb1 * (double)(c1 - c0) * nb0, st);
-      if ((r = trsm(st, LinvOf(s, 1), nb1, B + nb0, c1 - c0))) return r;
+      if ((r = trsm(st, LinvOf(s, 1), nb1, B + nb0, c1 - c0, dep))) return r;
     }
     if (m > ob) {
       ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);
-      r = mmr_dgemm_launch(ctx, st, m - ob, c1 - c0, ob, -1.0, P + ob, m, B, ld, 1.0, B + ob, ld);
+      r = mmr_dgemm_launch(ctx, st, m - ob, c1 - c0, ob, -1.0, P + ob, m, B, ld, 1.0, B + ob, ld, d_fail, dep);
       if (r) return r;
       mmr_prof_end(ctx, ps, 2.0 * (m - ob) * (double)(c1 - c0) * ob, st);
     }
     return 0;
   };
-  // broadcast record s on the side stream (overlaps the main stream's update of block s-1);
-  // ev[2 + (s&1)] marks its arrival
+  // broadcast record s on the side stream (overlaps the main stream's update of block s-1), then fold the
+  // owner's guard word into mine; ev[2 + (s&1)] marks the arrival
   auto bcast_record = [&](int s) -> int {
     const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
     if (R > 1) {
-      const int r = mmr_comm_bcast_bytes(ctx, rec[s & 1], sizeof(double) * (hdr_doubles + (size_t)m * ob), s % R, side);
+      const size_t bytes = sizeof(double) * (hdr_doubles + (size_t)m * ob);
+      const int pc = mmr_prof_begin(ctx, MMR_PROF_COMM, side);
+      const int r = mmr_comm_bcast_bytes(ctx, rec[s & 1], bytes, s % R, side);
       if (r) return r;
+      mmr_prof_end(ctx, pc, (double)bytes, side);
     }
+    lu_absorb_fail_kernel<<<1, 1, 0, side>>>(FailOf(s), d_fail);
+    MMR_CHECK_LAUNCH(ctx);
     MMR_CUDA(cudaEventRecord(ctx->ev[2 + (s & 1)], side));
     return 0;
   };
 
-  if (me == 0) {
-    rc = factor_and_pack(0, side);
-    if (rc) return rc;
-  }
-  rc = bcast_record(0);
-  if (rc) return rc;
-  for (int s = 0; s < S; ++s) {
-    const int kb = s * obw;
-    const int ob = min(obw, N - kb);
-    const int nb0 = min(NB, ob), nb1 = ob - nb0;
-    MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[2 + (s & 1)], 0));
-    // from here on the main stream no longer reads record s-1 = the buffer of record s+1
+  // One pass over the blocks from s0 on.  Entry state: every block before s0 is factored and applied
+  // everywhere, block s0 has received all earlier updates (first_inner = 1: and its panel 0 is done).
+  auto run = [&](int s0, int first_inner) -> int {
     MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
-    MMR_CUDA(cudaMemcpyAsync(d_ipiv + kb, IpivOf(s), sizeof(int) * ob, cudaMemcpyDeviceToDevice, st));
-    rc = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb, kb + nb0, pslot(s, 0));
-    if (rc) return rc;
-    if (nb1 > 0) {
-      rc = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb + nb0, kb + ob, pslot(s, 1));
-      if (rc) return rc;
+    MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));  // the side stream starts after everything queued so far
+    int r = 0;
+    if (me == s0 % R && (r = factor_and_pack(s0, side, first_inner))) return r;
+    if ((r = bcast_record(s0))) return r;
+    for (int s = s0; s < S; ++s) {
+      const int kb = s * obw;
+      const int ob = min(obw, N - kb);
+      const int nb0 = min(NB, ob), nb1 = ob - nb0;
+      MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[2 + (s & 1)], 0));
+      // from here on the main stream no longer reads record s-1 = the buffer of record s+1
+      MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
+      MMR_CUDA(cudaMemcpyAsync(d_ipiv + kb, IpivOf(s), sizeof(int) * ob, cudaMemcpyDeviceToDevice, st));
+      if ((r = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb, kb + nb0, pslot(s, 0), d_fail))) return r;
+      if (nb1 > 0 && (r = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb + nb0, kb + ob, pslot(s, 1), d_fail))) return r;
+      // my already-factored blocks (global index < s): interchanges only
+      const int nleft = (s > me) ? ((s - 1 - me) / R + 1) : 0;
+      {
+        const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
+        r = mmr_lu_laswp_apply(ctx, st, Al, ld, 0, nleft * obw, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1, d_fail,
+                               last_panel(s));
+        if (r) return r;
+        mmr_prof_end(ctx, ps, 32.0 * ob * (double)nleft * obw, st);
+      }
+      // my trailing blocks (global index > s)
+      const int first_trail = (s >= me) ? ((s - me) / R + 1) : 0;
+      const int ct0 = first_trail * obw, ct1 = ncols_local;
+      const bool have_next = s + 1 < S;
+      const bool own_next = have_next && ((s + 1) % R == me);
+      if (own_next) {
+        // look-ahead: bring my next block up to date first, then factor it on the side stream while
+        // the main stream updates the rest of my trailing columns
+        const int ob1 = min(obw, N - (s + 1) * obw);
+        if ((r = update_local(s, ct0, ct0 + ob1))) return r;
+        MMR_CUDA(cudaEventRecord(ctx->ev[0], st));
+        if ((r = update_local(s, ct0 + ob1, ct1))) return r;
+        MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
+        if ((r = factor_and_pack(s + 1, side, 0))) return r;
+      } else {
+        if ((r = update_local(s, ct0, ct1))) return r;
+        MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));
+      }
+      if (have_next && (r = bcast_record(s + 1))) return r;
     }
-    // my already-factored blocks (global index < s): interchanges only
-    const int nleft = (s > me) ? ((s - 1 - me) / R + 1) : 0;
-    {
-      const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
-      rc = mmr_lu_laswp_apply(ctx, st, Al, ld, 0, nleft * obw, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1);
-      if (rc) return rc;
-      mmr_prof_end(ctx, ps, 32.0 * ob * (double)nleft * obw, st);
-    }
-    // my trailing blocks (global index > s)
-    const int first_trail = (s >= me) ? ((s - me) / R + 1) : 0;
-    const int ct0 = first_trail * obw, ct1 = ncols_local;
-    const bool have_next = s + 1 < S;
-    const bool own_next = have_next && ((s + 1) % R == me);
-    if (own_next) {
-      // look-ahead: bring my next block up to date first, then factor it on the side stream while
-      // the main stream updates the rest of my trailing columns (enqueued first: the speculative
-      // panels make the host wait for the side stream)
-      const int ob1 = min(obw, N - (s + 1) * obw);
-      rc = update_local(s, ct0, ct0 + ob1);
-      if (rc) return rc;
-      MMR_CUDA(cudaEventRecord(ctx->ev[0], st));
-      rc = update_local(s, ct0 + ob1, ct1);
-      if (rc) return rc;
-      MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
-      rc = factor_and_pack(s + 1, side);
-      if (rc) return rc;
-    } else {
-      rc = update_local(s, ct0, ct1);
-      if (rc) return rc;
-      MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));
-    }
-    if (have_next) {
-      rc = bcast_record(s + 1);
-      if (rc) return rc;
-    }
-  }
-  // whatever follows on the main stream comes after everything on the side stream
-  MMR_CUDA(cudaEventRecord(ctx->ev[0], side));
-  MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[0], 0));
+    // whatever follows on the main stream comes after everything on the side stream
+    MMR_CUDA(cudaEventRecord(ctx->ev[0], side));
+    MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[0], 0));
+    return 0;
+  };
+
   int* h_info = (int*)ctx->hpin;
-  MMR_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-  MMR_CUDA(cudaStreamSynchronize(st));
-  if (info_out) *info_out = *h_info;  // only the owner of a zero pivot sees it; callers reduce over ranks
+  int s0 = 0, first_inner = 0;
+  for (;;) {
+    rc = run(s0, first_inner);
+    if (rc) return rc;
+    MMR_CUDA(cudaMemcpyAsync(h_info, d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MMR_CUDA(cudaStreamSynchronize(st));
+    if (!spec_on || h_info[1] == 0) break;
+    // a speculative panel was rejected at column kf (every rank holds the same guard word: it travels in
+    // the records): resume at its block with the pivoting kernels
+    const int kf = h_info[1] - 1;
+    spec_on = false;
+    s0 = kf / obw;
+    first_inner = (kf > s0 * obw) ? 1 : 0;
+    MMR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+  }
+  if (info_out) *info_out = h_info[0];  // only the owner of a zero pivot sees it; callers reduce over ranks
   return 0;
 }
 

@@ -90,7 +90,7 @@ __device__ __forceinline__ void cas128(u64* addr, u64 new_lo, u64 new_hi, u64& o
 template <bool INSERT>
 __device__ __forceinline__ u64 find_slot(const MatchParams& p, const PairKey& key, u64 me) {
   u64 h = hash_key(key) & p.mask;
-  for (long long probes = 0; probes <= (long long)p.mask; ++probes) {
+  for (u64 probes = 0; probes <= p.mask; ++probes) {
     const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(p.tab + 2 * h));  // L2: where the CAS lands
     u64 lo = cur.x, hi = cur.y;
     if (hi == 0) {  // empty (a valid key has bit 63 of hi set)
@@ -102,16 +102,17 @@ __device__ __forceinline__ u64 find_slot(const MatchParams& p, const PairKey& ke
         return h;
       }
     }
+    if (hi == key.hi && lo == 0) {
+      // The 16-byte vector load is not guaranteed single-copy atomic against the 128-bit CAS that publishes
+      // a slot: a reader can see the new `hi` next to a stale (zero) `lo`.  Such a slot may hold this key, a
+      // genuine key whose low word IS zero (pairs displaced along z only), or another key with the same
+      // high word.  Read it once more ATOMICALLY before comparing (a 128-bit CAS of 0 -> 0 returns the slot
+      // and cannot modify a published one).
+      cas128(p.tab + 2 * h, 0ull, 0ull, lo, hi);
+    }
     if (lo == key.lo && hi == key.hi) {
       if (INSERT && me < p.minrep[h]) atomicMin(&p.minrep[h], me);
       return h;
-    }
-    if (hi == key.hi && lo == 0 && key.lo != 0) {
-      // the 16-byte vector load is not guaranteed single-copy atomic against the 128-bit CAS that
-      // publishes a slot: a reader can see the new `hi` with a stale (zero) `lo`.  Look again instead
-      // of walking past a slot that may hold this very key (which would insert it a second time).
-      --probes;
-      continue;
     }
     h = (h + 1) & p.mask;
   }

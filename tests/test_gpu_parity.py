@@ -92,6 +92,18 @@ def test_assembly_matches_mpmath_known_answers(ctx, golden_dir):
         np.testing.assert_allclose(blk, ref, rtol=1e-12, atol=1e-15)
 
 
+def test_assembly_matches_mpmath_known_answers_for_rotated_sources(ctx, golden_dir):
+    """Rotated source cell (tests/golden/make_rotated_known_answers.py: global-frame surface-charge quadrature)."""
+    data = json.loads((golden_dir / "cuboid_rotated_known_answers.json").read_text())
+    for case in data["cases"]:
+        ref = np.array([[float(v) for v in row] for row in case["block_l_k"]])
+        pos = np.stack([np.zeros(3), np.array(case["offset"])])
+        quat = np.stack([np.array(case["quat"]), np.array((0.0, 0, 0, 1))])  # the target's own pose is irrelevant
+        dim = np.stack([np.array(case["dim"]), np.array((0.1, 0.2, 0.3))])
+        Nmat = assemble_numpy(ctx, pos, quat, dim)
+        np.testing.assert_allclose(Nmat[3:6, 0:3], ref, rtol=1e-12, atol=2e-15)  # target 1, source 0
+
+
 @pytest.mark.parametrize("shape", [(6, 6, 6), (5, 3, 7), (1, 1, 1), (1, 1, 2), (33, 1, 1)])
 def test_assembly_aligned_cells_vs_oracle(ctx, shape):
     pos, quat, dim = oref.mesh_cuboid_arrays((1e-3, 1.3e-3, 0.7e-3), shape)
@@ -790,3 +802,96 @@ def test_two_magnets_8000_full_size_vs_oracle(ctx, golden_dir):
     out = apply_demag(bench.make_collection("two_magnets_8000"))
     err = np.abs(bench.collection_polarizations(out) - gold).max() / np.abs(gold).max()
     assert err <= J_RTOL, err
+
+
+@pytest.mark.parametrize("nb", [128, 112, 96, 33, 1])
+def test_lu_diag_block_cluster_kernel_vs_numpy(ctx, nb):
+    """The one-launch diagonal-block step of the speculative panel (panel128.cuh): no-pivot LU + L^-1 + U^-1
+    against a numpy elimination, and the rejection of a block that needs an interchange."""
+    rng = np.random.default_rng(nb)
+    A = rng.normal(size=(nb, nb)) * 0.2
+    A[np.arange(nb), np.arange(nb)] += 2.0 + nb * 0.2  # diagonally dominant: every multiplier stays below 1
+    ld = nb + 5
+    dA = torch.zeros(nb, ld, dtype=torch.float64, device=ctx.device)  # column-major A = rows of this tensor
+    dA[:, :nb] = dev(ctx, A.T)
+    dS = torch.zeros(nb, ld, dtype=torch.float64, device=ctx.device)
+    dL = torch.zeros(nb, nb, dtype=torch.float64, device=ctx.device)
+    dU = torch.zeros(nb, nb, dtype=torch.float64, device=ctx.device)
+    assert ctx.lu_diag_block(dA, ld, nb, dS, ld, dL, dU) is False
+    LU = A.copy()
+    for j in range(nb):
+        LU[j + 1:, j] /= LU[j, j]
+        LU[j + 1:, j + 1:] -= np.outer(LU[j + 1:, j], LU[j, j + 1:])
+    L = np.tril(LU, -1) + np.eye(nb)
+    U = np.triu(LU)
+    got = dS[:, :nb].cpu().numpy().T
+    np.testing.assert_allclose(got, LU, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(dL.cpu().numpy().T, np.linalg.inv(L), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(dU.cpu().numpy().T, np.linalg.inv(U), rtol=1e-11, atol=1e-13)
+    if nb > 1:
+        B = A.copy()
+        B[nb // 2, nb // 2] = 1e-3  # the column below holds larger entries: partial pivoting would interchange
+        dA[:, :nb] = dev(ctx, B.T)
+        assert ctx.lu_diag_block(dA, ld, nb, dS, ld, dL, dU) is True
+
+
+# ---- FEM (ANSYS) datasets of the reference's docs through the OBJECT API (rotated Cuboids, Collections,
+#      Sensors with position paths) -- same fixtures and tolerances as tests/test_oracle_golden.py ---------------
+@pytest.mark.parametrize("solver", ["lu", "gmres"])
+def test_fem_softmag_dataset_through_the_object_api(golden_dir, solver):
+    from magpylib_material_response_b200 import Sensor
+    from test_oracle_golden import SOFTMAG_TOL, softmag_cells
+
+    fem = np.loadtxt(golden_dir / "femdata" / "FEMdata_test_softmag.csv", delimiter=",", skiprows=1)
+    cube1 = Cuboid(polarization=(0, 0, 1), dimension=(0.001, 0.001, 0.002))
+    cube1.move((0, 0, 0.0005))
+    cube1.susceptibility = 0.5
+    cube2 = Cuboid(polarization=(0, 0, 0), dimension=(0.001, 0.001, 0.001))
+    cube2.rotate_from_angax(angle=45, axis="y").move((0.0015, 0, 0))
+    cube2.susceptibility = 3999
+    coll = Collection(mesh_Cuboid(cube1, (6, 6, 12)), mesh_Cuboid(cube2, (8, 8, 8)), style_label="meshed")
+    sensors = [Sensor(position=np.linspace((-0.004, 0, z), (0.006, 0, z), 1001)) for z in (-0.001, -0.003, -0.005)]
+    out = apply_demag(coll, solver=solver, tol=1e-13)
+    B = out.getB(sensors)  # (path, sensor, 3)
+    assert B.shape == (1001, 3, 3)
+    for k in range(3):
+        np.testing.assert_allclose(B[:, k, 0], fem[:, 1 + 2 * k], rtol=0, atol=SOFTMAG_TOL[k])
+        np.testing.assert_allclose(B[:, k, 2], fem[:, 2 + 2 * k], rtol=0, atol=SOFTMAG_TOL[k])
+    # and the oracle on the same cells: solved polarizations within the north-star tolerance
+    pos, quat, dim, pol, chi = softmag_cells()
+    ref = oref.apply_demag_ref(pos, quat, dim, pol, chi, split=4)
+    got = np.array([s.polarization for s in out.sources_all])
+    assert np.abs(got - ref).max() <= J_RTOL * np.abs(ref).max()
+    assert out.getB(sensors[0]).shape == (1001, 3)
+
+
+def test_fem_three_cuboids_dataset_through_the_object_api(golden_dir):
+    from magpylib_material_response_b200 import Sensor, mesh_all
+    from test_oracle_golden import CUBOIDS_TOL, cuboids_cells
+
+    fem = np.loadtxt(golden_dir / "femdata" / "FEMdata_test_cuboids.csv", delimiter=",", skiprows=1)
+    cube1 = Cuboid(polarization=(0, 0, 1), dimension=(0.001, 0.001, 0.001))
+    cube1.move((-0.0015, 0, 0))
+    cube1.susceptibility = 0.3
+    cube2 = Cuboid(polarization=(0.9, 0, 0), dimension=(0.001, 0.001, 0.001))
+    cube2.rotate_from_angax(-45, "y").move((0, 0, 0.0002))
+    cube2.susceptibility = 1.0
+    mx, my = 0.6 * np.sin(np.deg2rad(30)), 0.6 * np.cos(np.deg2rad(30))
+    cube3 = Cuboid(polarization=(mx, my, 0), dimension=(0.001, 0.001, 0.002))
+    cube3.move((0.0016, 0, 0.0005)).rotate_from_angax(30, "z")
+    cube3.susceptibility = 0.5
+    coll = Collection(mesh_Cuboid(cube1, (5, 5, 5)), mesh_Cuboid(cube2, (5, 5, 5)), mesh_Cuboid(cube3, (5, 5, 10)))
+    sensor = Sensor(position=np.linspace((-0.004, 0, -0.001), (0.004, 0, -0.001), 301))
+    out = apply_demag(coll)
+    B = out.getB(sensor)
+    assert B.shape == (301, 3)
+    for k in range(3):
+        np.testing.assert_allclose(B[:, k], fem[:, 1 + k], rtol=0, atol=CUBOIDS_TOL[k])
+    pos, quat, dim, pol, chi = cuboids_cells()
+    ref = oref.apply_demag_ref(pos, quat, dim, pol, chi, split=4)
+    got = np.array([s.polarization for s in out.sources_all])
+    assert np.abs(got - ref).max() <= J_RTOL * np.abs(ref).max()
+    # the docs' own route: mesh_all over the un-meshed collection (volume-apportioned cell counts)
+    meshed = mesh_all(Collection(cube1.copy(), cube2.copy(), cube3.copy()), target_elems=400, per_child_elems=False)
+    B2 = apply_demag(meshed).getB(sensor)
+    assert np.abs(B2 - B).max() < 6e-4  # two different meshes of the same problem
