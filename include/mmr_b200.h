@@ -86,7 +86,7 @@ int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
                     int64_t* launches_out);
 /* Individual record durations (ms) of one class, in launch order; returns the count written. */
 int64_t mmr_ctx_profile_records(mmr_ctx* ctx, int kind, double* ms_out, int64_t cap);
-/* All records in launch order as a timeline: kind (| 0x100 for records of the side stream), start (ms after mmr_ctx_set_profiling(on)) and
+/* All records in launch order as a timeline: kind (| 0x100: side stream, | 0x200: communication stream), start (ms after mmr_ctx_set_profiling(on)) and
  * duration (ms) -- records of both streams of the context share one device clock.  Returns the count. */
 int64_t mmr_ctx_profile_timeline(mmr_ctx* ctx, int* kind_out, double* start_ms_out, double* dur_ms_out,
                                  int64_t cap);
@@ -151,7 +151,14 @@ int mmr_assemble_matched_rows(mmr_ctx* ctx, int64_t n, const double* d_pos, cons
  * partial pivoting of the column-major view Q^T = P L U), which keeps every pivot search
  * inside one row block -- the property the multi-GPU row sharding relies on.
  * d_ipiv: N int32 (device).  info_out (host, may be NULL): 0, or k>0 if pivot k-1 is exactly 0.
+ *
+ * Factor format.  The factors are consumed by mmr_lu_solve only.  When no panel of the factorization needed an
+ * interchange (always the case for the demag matrices Q = I - chi N), every diagonal panel block (128 columns,
+ * at multiples of 128) is stored as L11^-1 (strictly lower part) and U11^-1 (upper part) instead of L11 and U11,
+ * and bit 30 of d_ipiv[0] is set (MMR_LU_FORMAT_INVDIAG); the pivot index itself is d_ipiv[0] & (2^30 - 1).
+ * The solves on such factors are block products without substitution.  Otherwise plain LAPACK-style L\U.
  */
+#define MMR_LU_FORMAT_INVDIAG (1 << 30)
 int mmr_lu_factor(mmr_ctx* ctx, int64_t N, double* d_Q, int64_t ld, int32_t* d_ipiv,
                   int* info_out);
 /* Solves Q X = B for nrhs right-hand sides; d_B is row-major nrhs x N (each RHS contiguous),
@@ -165,6 +172,9 @@ int mmr_lu_solve(mmr_ctx* ctx, int64_t N, const double* d_LU, int64_t ld, const 
  * have interchanged rows (a multiplier above 1 in magnitude) or a pivot is zero; outputs are then undefined. */
 int mmr_lu_diag_block(mmr_ctx* ctx, const double* d_A, int64_t ld, int nb, double* d_S, int64_t lds,
                       double* d_Linv, double* d_Uinv, int* rejected_out);
+
+/* SM clock stamps (30 x int64) at the phase boundaries of the last mmr_lu_diag_block call (micro-benchmarks). */
+int mmr_lu_diag_block_clocks(mmr_ctx* ctx, long long* out30);
 
 /* C = alpha * op(A) op(B) + beta * C on the FP64 tensor-core (DMMA) path used by the LU
  * trailing update; exported for tests and the roofline measurement.  COLUMN-major (BLAS

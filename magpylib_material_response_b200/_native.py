@@ -91,6 +91,7 @@ _SIGNATURES = {
         [ctypes.c_void_p, _c_double_p, ctypes.c_int64, ctypes.c_int, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
          ctypes.POINTER(ctypes.c_int)],
     ),
+    "mmr_lu_diag_block_clocks": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "mmr_dgemm_nn": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, _c_double_p,
@@ -276,7 +277,8 @@ class Context:
         t0 = (ctypes.c_double * cap)()
         dt = (ctypes.c_double * cap)()
         n = self.lib.mmr_ctx_profile_timeline(self.handle, kinds, t0, dt, cap)
-        return [(self.PROF_KINDS[kinds[i] & 0xFF] + ("@side" if kinds[i] & 0x100 else ""), t0[i], dt[i]) for i in range(n)]
+        tag = ("", "@side", "@comm")
+        return [(self.PROF_KINDS[kinds[i] & 0xFF] + tag[(kinds[i] >> 8) & 3], t0[i], dt[i]) for i in range(n)]
 
     def profile_records(self, kind, cap=100000):
         buf = (ctypes.c_double * cap)()
@@ -341,6 +343,11 @@ class Context:
         _check(self.lib, self.lib.mmr_lu_diag_block(self.handle, _ptr(A), ld, nb, _ptr(S), lds, _ptr(Linv), _ptr(Uinv),
                                                     ctypes.byref(rej)))
         return bool(rej.value)
+
+    def lu_diag_block_clocks(self):
+        buf = (ctypes.c_longlong * 30)()
+        _check(self.lib, self.lib.mmr_lu_diag_block_clocks(self.handle, buf))
+        return list(buf)
 
     def dgemm_nn(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
         _check(self.lib, self.lib.mmr_dgemm_nn(self.handle, m, n, k, alpha, _ptr(A), lda, _ptr(B), ldb,

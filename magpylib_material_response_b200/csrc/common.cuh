@@ -37,7 +37,7 @@ struct mmr_ctx {
   bool profiling = false;
   struct ProfRec {
     int kind;
-    int side;  // 1: enqueued on the context's side (look-ahead) stream
+    int side;  // 0: main stream, 1: side (look-ahead) stream, 2: communication stream
     cudaEvent_t e0, e1;
     double units;
   };
@@ -54,6 +54,9 @@ struct mmr_ctx {
   int panel_cluster_max = -1;                          // largest launchable strip cluster (-1: not probed)
   bool panel_reg_ok = false;                           // non-portable cluster sizes allowed for the register strips
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // third stream + events of the distributed LU: broadcasts run beside the panel chain
+  cudaStream_t comm = nullptr;
+  cudaEvent_t evd[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 void mmr_set_error(const char* fmt, ...);

@@ -69,7 +69,7 @@ int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s) {
   if (!ctx->profiling) return -1;
   mmr_ctx::ProfRec r;
   r.kind = kind;
-  r.side = (s == ctx->side) ? 1 : 0;
+  r.side = (s == ctx->side) ? 1 : ((ctx->comm && s == ctx->comm) ? 2 : 0);
   r.e0 = prof_event(ctx);
   r.e1 = prof_event(ctx);
   r.units = 0.0;
@@ -107,13 +107,14 @@ extern "C" int64_t mmr_ctx_profile_timeline(mmr_ctx* ctx, int* kind_out, double*
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->side) cudaStreamSynchronize(ctx->side);
+  if (ctx->comm) cudaStreamSynchronize(ctx->comm);
   int64_t cnt = 0;
   for (auto& r : ctx->prof) {
     if (cnt >= cap) break;
     float t0 = 0.f, dt = 0.f;
     if (cudaEventElapsedTime(&t0, ctx->prof_base, r.e0) != cudaSuccess) continue;
     if (cudaEventElapsedTime(&dt, r.e0, r.e1) != cudaSuccess) continue;
-    if (kind_out) kind_out[cnt] = r.kind | (r.side ? 0x100 : 0);
+    if (kind_out) kind_out[cnt] = r.kind | (r.side << 8);
     if (start_ms_out) start_ms_out[cnt] = t0;
     if (dur_ms_out) dur_ms_out[cnt] = dt;
     ++cnt;
@@ -188,10 +189,12 @@ extern "C" int mmr_ctx_create(int device, void* stream, mmr_ctx** out) {
     int lo = 0, hi = 0;
     MMR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     MMR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));  // panel look-ahead stream
+    MMR_CUDA(cudaStreamCreateWithPriority(&c->comm, cudaStreamNonBlocking, hi));  // broadcasts of the distributed LU
     const char* la = getenv("MMR_LU_LOOKAHEAD");
     c->lookahead = !(la && la[0] == '0');
   }
   for (int i = 0; i < 4; ++i) MMR_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) MMR_CUDA(cudaEventCreateWithFlags(&c->evd[i], cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -213,7 +216,10 @@ extern "C" int mmr_ctx_destroy(mmr_ctx* ctx) {
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->evd[i]) cudaEventDestroy(ctx->evd[i]);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->comm) cudaStreamDestroy(ctx->comm);
   delete ctx;
   return 0;
 }

@@ -48,11 +48,27 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // stays in a consistent "everything before the failed panel applied" state the host can resume from.
 __device__ __forceinline__ bool lu_poisoned(int failword, int dep) { return failword != 0 && failword - 1 <= dep; }
 __device__ __forceinline__ int lu_failword(const int* fail) { return fail ? __ldcg(fail) : 0; }
+// (the GEMM kernels take one more word, check_val: when non-zero, a stored value with |c| > 1 (or NaN) writes
+// check_val into *fail -- the a-posteriori test of a speculative panel's multipliers, fused into the epilogue
+// of the L21 = A21 U11^-1 product)
 
 // Sign flip on the integer pipe (a DADD/DMUL negation would compete with the DMMAs for the FP64 pipe).
 __device__ __forceinline__ double flip_sign(double x) {
   return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
+
+// A second, independent product that shares a launch with the first one (blockIdx.z == 1): the LU panel chain
+// is a sequence of small dependent kernels whose cost is launch + scheduling latency, so two products that
+// depend on the same predecessor (L21 = A21 U11^-1 and U12 = L11^-1 A12) go out together.  m == 0: none.
+struct GemmAlt {
+  int m = 0, n = 0, k = 0;
+  const double* A = nullptr;
+  int64_t lda = 0;
+  const double* B = nullptr;
+  int64_t ldb = 0;
+  double* C = nullptr;
+  int64_t ldc = 0;
+};
 
 // ALIGNED16: A, B 16-byte aligned with even leading dimensions (cp.async 16 B); otherwise 8 B.
 // SUBTRACT : the LU form C <- C - A*B (alpha = -1, beta = 1).  The C tile is loaded straight into
@@ -63,7 +79,7 @@ template <bool ALIGNED16, bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                     const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                    int64_t ldc, const int* __restrict__ fail, int dep) {
+                    int64_t ldc, int* __restrict__ fail, int dep, int check_val) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
@@ -184,6 +200,7 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
   cp_async_wait<0>();
   if (lu_poisoned(failword, dep)) return;
+  bool viol = false;  // check_val != 0: the speculation check |c| <= 1 on every stored value (LU panel's L21)
 
   // epilogue: thread holds rows (lane>>2), cols 2*(lane&3) + {0,1} of each 8x8 fragment
 #pragma unroll
@@ -200,13 +217,16 @@ __global__ void __launch_bounds__(THREADS, 2)
           if (SUBTRACT) {
             *cp = flip_sign(acc[f][g][e]);
           } else {
-            const double v = alpha * acc[f][g][e];
-            *cp = (beta == 0.0) ? v : (v + beta * (*cp));
+            double v = alpha * acc[f][g][e];
+            if (beta != 0.0) v += beta * (*cp);
+            *cp = v;
+            if (!(fabs(v) <= 1.0)) viol = true;
           }
         }
       }
     }
   }
+  if (check_val != 0 && viol) atomicCAS(fail, 0, check_val);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -225,14 +245,21 @@ template <bool SUBTRACT>
 __global__ void __launch_bounds__(THREADS, 2)
     dgemm_nn_fast_kernel(int m, int n, int k, double alpha, const double* __restrict__ A, int64_t lda,
                          const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                         int64_t ldc, int prefetch_dist, const int* __restrict__ fail, int dep) {
+                         int64_t ldc, int prefetch_dist, int* __restrict__ fail, int dep, int check_val,
+                         const GemmAlt alt) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
   const int failword = lu_failword(fail);  // consumed before the first store (epilogue)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;
+  if (blockIdx.z != 0) {  // the second product of a paired launch (block-uniform)
+    m = alt.m, n = alt.n, k = alt.k;
+    A = alt.A, lda = alt.lda, B = alt.B, ldb = alt.ldb, C = alt.C, ldc = alt.ldc;
+    check_val = 0;
+  }
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (m0 >= m || n0 >= n) return;  // (the grid of a paired launch covers the larger product)
   const int KT = k / BK;
 
   double acc[4][4][2];
@@ -356,6 +383,7 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
   cp_async_wait<0>();
   if (lu_poisoned(failword, dep)) return;
+  bool viol = false;
 
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
@@ -371,12 +399,15 @@ __global__ void __launch_bounds__(THREADS, 2)
           if (SUBTRACT) {
             *cp = flip_sign(acc[f][g][e]);
           } else {
-            const double v = alpha * acc[f][g][e];
-            *cp = (beta == 0.0) ? v : (v + beta * (*cp));
+            double v = alpha * acc[f][g][e];
+            if (beta != 0.0) v += beta * (*cp);
+            *cp = v;
+            if (!(fabs(v) <= 1.0)) viol = true;
           }
         }
       }
   }
+  if (check_val != 0 && viol) atomicCAS(fail, 0, check_val);
 }
 
 }  // namespace mmr_gemm
@@ -384,4 +415,5 @@ __global__ void __launch_bounds__(THREADS, 2)
 // host-side launcher (defined in lu.cu)
 int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                     double* C, int64_t ldc, const int* fail = nullptr, int dep = 0);
+                     double* C, int64_t ldc, int* fail = nullptr, int dep = 0, int check_val = 0,
+                     const mmr_gemm::GemmAlt* alt = nullptr);

@@ -17,6 +17,7 @@
 
 #include <cstdlib>
 
+#include "comm.h"
 #include "dgemm.cuh"
 #include "panel128.cuh"
 
@@ -797,13 +798,18 @@ __global__ void lu_gather_kernel(const double* __restrict__ v, const int* __rest
 
 int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                     double* C, int64_t ldc, const int* fail, int dep) {
+                     double* C, int64_t ldc, int* fail, int dep, int check_val, const mmr_gemm::GemmAlt* alt) {
   using namespace mmr_gemm;
-  if (m <= 0 || n <= 0) return 0;
+  if (alt && (alt->m <= 0 || alt->n <= 0)) alt = nullptr;
+  if (m <= 0 || n <= 0) {
+    if (!alt) return 0;
+    return mmr_dgemm_launch(ctx, s, alt->m, alt->n, alt->k, alpha, alt->A, alt->lda, alt->B, alt->ldb, beta, alt->C, alt->ldc,
+                            fail, dep, 0, nullptr);
+  }
   const bool aligned = (((uintptr_t)A | (uintptr_t)B) % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
   const bool subtract = (alpha == -1.0 && beta == 1.0);
   typedef void (*kern_t)(int, int, int, double, const double*, int64_t, const double*, int64_t, double,
-                         double*, int64_t, const int*, int);
+                         double*, int64_t, int*, int, int);
   static const kern_t kerns[4] = {dgemm_nn_kernel<false, false>, dgemm_nn_kernel<false, true>,
                                   dgemm_nn_kernel<true, false>, dgemm_nn_kernel<true, true>};
   const int which = (aligned ? 2 : 0) + (subtract ? 1 : 0);
@@ -823,17 +829,33 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     const char* e = getenv("MMR_DGEMM_PREFETCH");
     prefetch_on = (e && e[0] == '0') ? 0 : 1;
   }
-  if (fast && aligned && k > 0 && k % BK == 0) {
+  const bool fast_ok = fast && aligned && k > 0 && k % BK == 0;
+  if (alt) {
+    // paired launch: both products on the fast path, same alpha / beta; otherwise one after the other
+    const bool alt_ok = (((uintptr_t)alt->A | (uintptr_t)alt->B) % 16 == 0) && (alt->lda % 2 == 0) && (alt->ldb % 2 == 0) &&
+                        alt->k > 0 && alt->k % BK == 0;
+    if (!(fast_ok && alt_ok && !subtract)) {
+      int r = mmr_dgemm_launch(ctx, s, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, fail, dep, check_val, nullptr);
+      if (r) return r;
+      return mmr_dgemm_launch(ctx, s, alt->m, alt->n, alt->k, alpha, alt->A, alt->lda, alt->B, alt->ldb, beta, alt->C,
+                              alt->ldc, fail, dep, 0, nullptr);
+    }
+    grid.x = std::max(grid.x, (unsigned)ceil_div64(alt->m, BM));
+    grid.y = std::max(grid.y, (unsigned)ceil_div64(alt->n, BN));
+    grid.z = 2;
+  }
+  const GemmAlt alt_v = alt ? *alt : GemmAlt();
+  if (fast_ok) {
     // L2 prefetch distance for the C tiles: the number of CTAs resident at once (2 per SM)
-    const int pf = (prefetch_on && ntiles > 2 * (int64_t)ctx->sm_count) ? 2 * ctx->sm_count : 0;
+    const int pf = (prefetch_on && !alt && ntiles > 2 * (int64_t)ctx->sm_count) ? 2 * ctx->sm_count : 0;
     if (subtract)
-      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf, fail, dep);
+      dgemm_nn_fast_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf, fail, dep, check_val, alt_v);
     else
-      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf, fail, dep);
+      dgemm_nn_fast_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, pf, fail, dep, check_val, alt_v);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }
-  kerns[which]<<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, fail, dep);
+  kerns[which]<<<grid, THREADS, SMEM_BYTES, s>>>((int)m, (int)n, (int)k, alpha, A, lda, B, ldb, beta, C, ldc, fail, dep, check_val);
   MMR_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -1253,7 +1275,28 @@ __global__ void __launch_bounds__(256)
     const int64_t r = e % m, c = e / m;
     A[(kb + c) * ld + kb + r] = S[c * lds + r];
   }
-  if (blockIdx.x == 0 && threadIdx.x < nb) ipiv[kb + threadIdx.x] = kb + threadIdx.x;
+  if (ipiv && blockIdx.x == 0 && threadIdx.x < nb) ipiv[kb + threadIdx.x] = kb + threadIdx.x;
+}
+
+// Dst[r + c*ldd] = Src[r + c*lds] for r < rows, c < cols, unless a panel starting at or before `dep` was rejected
+__global__ void __launch_bounds__(256)
+    lu_copy_guarded_kernel(const double* __restrict__ Src, int64_t lds, int rows, int cols, double* __restrict__ Dst,
+                           int64_t ldd, const int* __restrict__ fail, int dep) {
+  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), dep)) return;
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e % rows, c = e / rows;
+    Dst[c * ldd + r] = Src[c * lds + r];
+  }
+}
+
+// identity pivots for the columns [kb, kb + n) of a speculative block, into up to two arrays
+__global__ void lu_fill_ipiv_kernel(int* __restrict__ p0, int* __restrict__ p1, int kb, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    if (p0) p0[i] = kb + i;
+    if (p1) p1[i] = kb + i;
+  }
 }
 
 }  // namespace
@@ -1267,7 +1310,8 @@ size_t mmr_lu_spec_scratch_bytes() { return sizeof(double) * NB * NB + 256; }  /
 // written, and every later operation that depends on it skips its stores (lu_poisoned) -- the host finds out
 // when it reads *d_fail at the end and resumes from that panel with the pivoting kernels.
 int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, int N, int kb, int nb, int* d_ipiv,
-                      double* S, double* Linv, void* d_spec, int* d_fail) {
+                      double* S, int64_t lds, double* Linv, void* d_spec, int* d_fail, bool commit,
+                      const mmr_gemm::GemmAlt* with_l21 = nullptr) {
   const size_t inv_smem = ((size_t)TINV_COLS * (NB + 1) + (size_t)NB * (NB + 1)) * sizeof(double);
   {
     const int rc0 = mmr_func_smem(ctx, (const void*)lu_tri_inv_kernel, inv_smem);
@@ -1282,33 +1326,35 @@ int mmr_lu_panel_spec(mmr_ctx* ctx, cudaStream_t strm, double* A, int64_t ld, in
   }
   const int pidx = mmr_prof_begin(ctx, MMR_PROF_PANEL, strm);
   if (panel_v1) {
-    lu_diag_nopiv_tile_kernel<<<1, 512, 0, strm>>>(A, ld, kb, nb, S, m, d_fail);
+    lu_diag_nopiv_tile_kernel<<<1, 512, 0, strm>>>(A, ld, kb, nb, S, lds, d_fail);
     MMR_CHECK_LAUNCH(ctx);
     const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
-    lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, strm>>>(S, m, nb, Linv, Uinv, d_fail, kb);
+    lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, strm>>>(S, lds, nb, Linv, Uinv, d_fail, kb);
     MMR_CHECK_LAUNCH(ctx);
   } else {
     // one cluster launch: blocked no-pivot LU of the diagonal block + both triangular inverses (panel128.cuh)
     const int rc1 = mmr_func_smem(ctx, (const void*)mmr_panel::lu_diag_inv_cluster_kernel, mmr_panel::PANEL_SMEM);
     if (rc1) return rc1;
     mmr_panel::lu_diag_inv_cluster_kernel<<<mmr_panel::PCLUSTER, mmr_panel::PTHREADS, mmr_panel::PANEL_SMEM, strm>>>(
-        A, ld, kb, nb, S, m, Linv, Uinv, d_fail);
+        A, ld, kb, nb, S, lds, Linv, Uinv, d_fail, nullptr);
     MMR_CHECK_LAUNCH(ctx);
   }
   mmr_prof_end(ctx, pidx, (double)nb, strm);
   if (m > nb) {
     const int pg = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
+    // L21 = A21 U11^-1 with the speculation check (every multiplier |l| <= 1) fused into the epilogue
+    // (with_l21: a second product that depends on this panel's diagonal block only rides in the same launch)
     int rc = mmr_dgemm_launch(ctx, strm, m - nb, nb, nb, 1.0, A + (int64_t)kb * ld + kb + nb, ld, Uinv, nb, 0.0,
-                              S + nb, m, d_fail, kb);
+                              S + nb, lds, d_fail, kb, kb + 1, with_l21);
     if (rc) return rc;
     mmr_prof_end(ctx, pg, 2.0 * (m - nb) * (double)nb * nb, strm);
-    const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)(m - nb) * nb, 256 * 8));
-    lu_spec_check_kernel<<<g, 256, 0, strm>>>(S, m, nb, m, nb, d_fail, kb);
-    MMR_CHECK_LAUNCH(ctx);
+  } else if (with_l21) {
+    int rc = mmr_dgemm_launch(ctx, strm, 0, 0, 0, 1.0, nullptr, 0, nullptr, 0, 0.0, nullptr, 0, d_fail, kb, 0, with_l21);
+    if (rc) return rc;
   }
-  {
+  if (commit) {
     const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)m * nb, 256 * 8));
-    lu_spec_commit_kernel<<<g, 256, 0, strm>>>(S, m, m, nb, A, ld, kb, d_ipiv, d_fail);
+    lu_spec_commit_kernel<<<g, 256, 0, strm>>>(S, lds, m, nb, A, ld, kb, d_ipiv, d_fail);
     MMR_CHECK_LAUNCH(ctx);
   }
   return 0;
@@ -1323,20 +1369,39 @@ extern "C" int mmr_lu_diag_block(mmr_ctx* ctx, const double* d_A, int64_t ld, in
   MMR_ARG(nb >= 1 && nb <= NB && ld >= nb && lds >= nb, "bad block size / leading dimension");
   MMR_ARG(d_A && d_S && d_Linv && d_Uinv, "NULL pointer");
   DeviceGuard g(ctx->device);
-  int rc = mmr_ws_reserve(ctx, 256);
+  int rc = mmr_ws_reserve(ctx, 512);
   if (rc) return rc;
-  rc = mmr_hpin_reserve(ctx, 256);
+  rc = mmr_hpin_reserve(ctx, 512);
   if (rc) return rc;
   int* d_fail = (int*)ctx->ws;
-  MMR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
-  rc = mmr_func_smem(ctx, (const void*)mmr_panel::lu_diag_inv_cluster_kernel, mmr_panel::PANEL_SMEM);
-  if (rc) return rc;
-  mmr_panel::lu_diag_inv_cluster_kernel<<<mmr_panel::PCLUSTER, mmr_panel::PTHREADS, mmr_panel::PANEL_SMEM, ctx->stream>>>(
-      d_A, ld, 0, nb, d_S, lds, d_Linv, d_Uinv, d_fail);
-  MMR_CHECK_LAUNCH(ctx);
+  MMR_CUDA(cudaMemsetAsync(d_fail, 0, 512, ctx->stream));
+  const char* v1 = getenv("MMR_LU_PANEL_V1");
+  if (v1 && v1[0] == '1') {  // the round-1 kernel pair, for A/B timing
+    const size_t smem = ((size_t)TINV_COLS * (nb + 1) + (size_t)nb * (nb + 1)) * sizeof(double);
+    rc = mmr_func_smem(ctx, (const void*)lu_tri_inv_kernel, ((size_t)TINV_COLS * (NB + 1) + (size_t)NB * (NB + 1)) * sizeof(double));
+    if (rc) return rc;
+    lu_diag_nopiv_tile_kernel<<<1, 512, 0, ctx->stream>>>(d_A, ld, 0, nb, d_S, lds, d_fail);
+    MMR_CHECK_LAUNCH(ctx);
+    lu_tri_inv_kernel<<<dim3((unsigned)ceil_div64(nb, TINV_COLS), 2), 256, smem, ctx->stream>>>(d_S, lds, nb, d_Linv, d_Uinv, d_fail, 0);
+    MMR_CHECK_LAUNCH(ctx);
+  } else {
+    rc = mmr_func_smem(ctx, (const void*)mmr_panel::lu_diag_inv_cluster_kernel, mmr_panel::PANEL_SMEM);
+    if (rc) return rc;
+    mmr_panel::lu_diag_inv_cluster_kernel<<<mmr_panel::PCLUSTER, mmr_panel::PTHREADS, mmr_panel::PANEL_SMEM, ctx->stream>>>(
+        d_A, ld, 0, nb, d_S, lds, d_Linv, d_Uinv, d_fail, (long long*)((char*)ctx->ws + 64));
+    MMR_CHECK_LAUNCH(ctx);
+    MMR_CUDA(cudaMemcpyAsync((char*)ctx->hpin + 8, (char*)ctx->ws + 64, 30 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   MMR_CUDA(cudaMemcpyAsync(ctx->hpin, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   MMR_CUDA(cudaStreamSynchronize(ctx->stream));
   if (rejected_out) *rejected_out = (*(int*)ctx->hpin != 0) ? 1 : 0;
+  return 0;
+}
+
+// SM clock stamps of the last mmr_lu_diag_block call (phase boundaries of the cluster kernel; micro-benchmarks)
+extern "C" int mmr_lu_diag_block_clocks(mmr_ctx* ctx, long long* out30) {
+  MMR_ARG(ctx != nullptr && out30 != nullptr && ctx->hpin != nullptr, "no diagonal-block call recorded");
+  memcpy(out30, (char*)ctx->hpin + 8, 30 * sizeof(long long));
   return 0;
 }
 
@@ -1536,6 +1601,247 @@ int mmr_lu_trtri(mmr_ctx* ctx, cudaStream_t strm, const double* L, int64_t ldl, 
   return mmr_lu_trsm(ctx, strm, L, ldl, nb, X, nb, nb);
 }
 
+// =======================================================================================
+// "Inverse format" of a fully speculative factorization and the block sweeps that use it.
+//
+// When no panel was rejected, the factorization ends by overwriting every diagonal panel block L11\U11 (<= 128
+// wide) with L11^-1 (strictly lower part, unit diagonal implied) and U11^-1 (upper part) -- both were computed
+// for the panel anyway -- and sets LU_FORMAT_INVDIAG in ipiv[0].  The triangular solves then need no
+// substitution at all: a block of the solution is a pair of small matrix-vector products, and one launch per
+// outer block does (i) the update of every later (earlier) column with the block that just became final and
+// (ii), in CTA 0, the finishing of the next block.  One launch and -- on several GPUs -- one small broadcast
+// per block instead of a dependent gemv -> diagonal-solve -> gemv -> diagonal-solve chain.
+// Factorizations that needed interchanges keep the plain format and the substitution kernels above (an
+// explicit inverse of a pivoted U11 would cost backward stability).
+// =======================================================================================
+constexpr int LU_FORMAT_INVDIAG = 1 << 30;
+constexpr int LU_IPIV_MASK = LU_FORMAT_INVDIAG - 1;
+
+namespace {
+
+// panel slot q of the inverse stash: [L^-1 (nb x nb, ld nb) | U^-1 (nb x nb, ld nb)], 2 * NB * NB doubles
+__global__ void __launch_bounds__(256)
+    lu_store_inverses_kernel(double* __restrict__ Al, int64_t ld, const double* __restrict__ stash, int npanels,
+                             int N, int obw, int R, int me, const int* __restrict__ fail) {
+  if (*fail != 0) return;  // a panel was rejected: the factors stay in plain format
+  const int q = blockIdx.x;
+  if (q >= npanels) return;
+  // panel q of this rank: local block j = q / 2 (global block me + j R), inner panel q % 2
+  const int j = q >> 1, inner = q & 1;
+  const int t = me + j * R;
+  const int kb0 = t * obw;
+  if (kb0 >= N) return;
+  const int ob = min(obw, N - kb0), nb0 = min(NB, ob);
+  const int nb = inner ? ob - nb0 : nb0;
+  if (nb <= 0) return;
+  const int off = inner ? nb0 : 0;  // offset of the panel inside its block
+  const double* Li = stash + (size_t)q * 2 * NB * NB;
+  const double* Ui = Li + (size_t)NB * NB;
+  double* D = Al + (int64_t)(j * obw + off) * ld + kb0 + off;  // local column of the panel, global row
+  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+    const int r = e % nb, c = e / nb;
+    D[(int64_t)c * ld + r] = (r > c) ? Li[c * nb + r] : Ui[c * nb + r];
+  }
+}
+
+__global__ void lu_set_format_kernel(int* __restrict__ ipiv, const int* __restrict__ fail) {
+  if (*fail == 0) ipiv[0] |= LU_FORMAT_INVDIAG;
+}
+
+// One step of the block sweeps on inverse-format factors (see above).  Global column c of block t = c / obw lives
+// at local column (t / R) * obw + c % obw of the owner t % R; rows are global.
+//   s_done : block whose piece of b is final (-1: none)      s_next : block CTA 0 finishes now (-1: none; owned)
+//   [far_lo, far_hi) : my local columns that receive the update by block s_done (CTAs 1..)
+template <bool FWD>
+__global__ void __launch_bounds__(1024)
+    lu_sweep_kernel(const double* __restrict__ Al, int64_t ld, int N, int obw, int R, int me, int s_done, int s_next,
+                    int far_lo, int far_hi, double* __restrict__ b) {
+  __shared__ double xs[2 * NB], ys[2 * NB], zs[2 * NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int u0 = s_done >= 0 ? s_done * obw : 0;
+  const int nu = s_done >= 0 ? min(obw, N - u0) : 0;
+  if (blockIdx.x != 0) {
+    // far columns: a warp takes four columns per pass -- 32 independent loads per lane in flight before the
+    // first reduction (one column per short-lived warp kept the memory pipeline at ~10 % of its bandwidth)
+    const int nwarps = (gridDim.x - 1) * 32;
+    for (int base = far_lo + 4 * ((blockIdx.x - 1) * 32 + warp); base < far_hi; base += 4 * nwarps) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int i = lane + 32 * t;
+        if (i < nu) {
+          const double xv = b[u0 + i];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (base + c < far_hi) acc[c] = fma(Al[(int64_t)(base + c) * ld + u0 + i], xv, acc[c]);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+      if (lane < 4 && base + lane < far_hi) {
+        const int lc = base + lane;
+        const int g = ((lc / obw) * R + me) * obw + lc % obw;
+        const double a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+        if (g < N) b[g] -= a;
+      }
+    }
+    return;
+  }
+  if (s_next < 0) return;
+  const int d0 = s_next * obw;
+  const int nd = min(obw, N - d0), na = min(NB, nd);
+  const double* blk = Al + (int64_t)((s_next / R) * obw) * ld;  // local column of global column d0
+  for (int i = tid; i < nu; i += blockDim.x) xs[i] = b[u0 + i];
+  __syncthreads();
+  // Warp w owns the columns j = w + 32 c, c < 8, of the block.  A product phase is latency bound (a handful of
+  // DRAM round trips), so every lane first issues the loads of ALL eight columns and only then reduces: one
+  // memory latency per phase instead of one per column.
+  //   sums[c] = sum_{r in [lo(j), hi(j))} A[row0 + r, d0 + j] * v[r]
+  auto dots = [&](int row0, auto lo_of, auto hi_of, const double* v, double (&sums)[8]) {
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int r = lane + 32 * t;
+      const double vr = v[r];  // (v has 256 readable entries; out-of-range rows are masked below)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int j = warp + 32 * c;
+        if (j < nd && r >= lo_of(j) && r < hi_of(j)) acc[c] = fma(blk[(int64_t)j * ld + row0 + r], vr, acc[c]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sums[c] = acc[c];
+  };
+  double sm[8];
+  // (1) the update by block s_done
+  dots(u0, [&](int) { return 0; }, [&](int) { return nu; }, xs, sm);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int j = warp + 32 * c;
+    if (lane == 0 && j < nd) ys[j] = b[d0 + j] - sm[c];
+  }
+  __syncthreads();
+  // (2) the block itself: two panels a = [0, na), q = [na, nd) with inverted diagonal blocks
+  if (FWD) {
+    // w_a = U_aa^-T y_a   and, for the columns of q, the part of U_qq^-T y_q ... no: y_q is not final yet
+    dots(d0, [&](int) { return 0; }, [&](int j) { return j < na ? j + 1 : 0; }, ys, sm);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 32 * c;
+      if (lane == 0 && j < na) zs[j] = sm[c];
+    }
+    __syncthreads();
+    dots(d0, [&](int) { return 0; }, [&](int j) { return j >= na ? na : 0; }, zs, sm);  // y_q -= U_aq^T w_a
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 32 * c;
+      if (lane == 0 && j >= na && j < nd) ys[j] -= sm[c];
+    }
+    __syncthreads();
+    dots(d0, [&](int) { return na; }, [&](int j) { return j >= na ? j + 1 : 0; }, ys, sm);  // w_q = U_qq^-T y_q
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 32 * c;
+      if (lane == 0 && j >= na && j < nd) zs[j] = sm[c];
+    }
+  } else {
+    dots(d0, [&](int j) { return j + 1; }, [&](int j) { return j >= na ? nd : 0; }, ys, sm);  // v_q = L_qq^-T y_q
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 32 * c;
+      if (lane == 0 && j >= na && j < nd) zs[j] = ys[j] + sm[c];
+    }
+    __syncthreads();
+    dots(d0, [&](int) { return na; }, [&](int j) { return j < na ? nd : 0; }, zs, sm);  // y_a -= L_qa^T v_q
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 32 * c;
+      if (lane == 0 && j < na) ys[j] -= sm[c];
+    }
+    __syncthreads();
+    dots(d0, [&](int j) { return j + 1; }, [&](int j) { return j < na ? na : 0; }, ys, sm);  // v_a = L_aa^-T y_a
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 32 * c;
+      if (lane == 0 && j < na) zs[j] = ys[j] + sm[c];
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < nd; j += blockDim.x) b[d0 + j] = zs[j];
+}
+
+}  // namespace
+
+// Triangular solves U^T w = b, L^T v = w on inverse-format factors (LU_FORMAT_INVDIAG), in place on d_b.
+// obw: width of the two-panel blocks the factorization used (256 on one GPU, 3 * tgt_block distributed); R, me:
+// block-cyclic ownership (1, 0 on one GPU); bcast: broadcast every finished block (R > 1).
+static int lu_sweeps_inv(mmr_ctx* ctx, cudaStream_t st, int N, int obw, int R, int me, const double* Al, int64_t ld,
+                         int ncols_local, double* d_b) {
+  const int S = (int)ceil_div64(N, obw);
+  auto step = [&](bool fwd, int s_done, int s_next_global) -> int {
+    // my columns that receive the update by s_done, and whether I finish s_next
+    const bool own_next = s_next_global >= 0 && s_next_global % R == me;
+    int far_lo = 0, far_hi = 0;
+    if (s_done >= 0) {
+      if (fwd) {
+        int jlo = (s_done >= me) ? (s_done - me) / R + 1 : 0;  // my blocks with global index <= s_done
+        if (own_next) ++jlo;                                  // CTA 0 takes that one
+        far_lo = jlo * obw, far_hi = ncols_local;
+      } else {
+        int nleft = (s_done > me) ? (s_done - 1 - me) / R + 1 : 0;  // my blocks with global index < s_done
+        if (own_next) --nleft;
+        far_lo = 0, far_hi = nleft * obw;
+      }
+    }
+    const int nfar = std::max(0, far_hi - far_lo);
+    if (!own_next && nfar == 0) return 0;
+    // CTA 0 + up to one far CTA per remaining SM (32 warps x 4 columns per pass each)
+    const unsigned grid = 1 + (unsigned)std::min<int64_t>(ctx->sm_count - 1, ceil_div64(nfar, 128));
+    if (fwd)
+      lu_sweep_kernel<true><<<grid, 1024, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
+                                                  far_hi, d_b);
+    else
+      lu_sweep_kernel<false><<<grid, 1024, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
+                                                   far_hi, d_b);
+    MMR_CHECK_LAUNCH(ctx);
+    return 0;
+  };
+  auto bcast = [&](int s) -> int {
+    if (R <= 1) return 0;
+    const int kb = s * obw, ob = std::min(obw, N - kb);
+    const int pc = mmr_prof_begin(ctx, MMR_PROF_COMM, st);
+    const int r = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * ob, s % R, st);
+    mmr_prof_end(ctx, pc, 8.0 * ob, st);
+    return r;
+  };
+  int rc = 0;
+  if ((rc = step(true, -1, 0)) || (rc = bcast(0))) return rc;
+  for (int s = 0; s + 1 < S; ++s)
+    if ((rc = step(true, s, s + 1)) || (rc = bcast(s + 1))) return rc;
+  if ((rc = step(false, -1, S - 1)) || (rc = bcast(S - 1))) return rc;
+  for (int s = S - 1; s >= 1; --s)
+    if ((rc = step(false, s, s - 1)) || (rc = bcast(s - 1))) return rc;
+  return 0;
+}
+
+// width of the outer blocks of the single-GPU factorization (two 128-column panels unless MMR_LU_OUTER=1)
+static int lu_outer_block() {
+  static int outer_mult = -1;
+  if (outer_mult < 0) {
+    const char* e = getenv("MMR_LU_OUTER");  // 1: rank-128 updates (one panel per outer block), 2: rank-256
+    outer_mult = (e && e[0] == '1') ? 1 : 2;
+  }
+  return outer_mult * NB;
+}
+
 // Single-GPU driver.  Two-level blocking: panels of NB = 128 columns are factored in pairs (an
 // "outer block" of OB = 256 columns), and the trailing matrix receives ONE rank-256 DMMA update per
 // outer block instead of two rank-128 updates: half the C read-modify-write traffic and half the
@@ -1552,12 +1858,7 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   MMR_ARG(d_Q && d_ipiv, "NULL matrix/pivot pointer");
   DeviceGuard g(ctx->device);
   const int N = (int)N64;
-  static int outer_mult = -1;
-  if (outer_mult < 0) {
-    const char* e = getenv("MMR_LU_OUTER");  // 1: rank-128 updates (one panel per outer block), 2: rank-256
-    outer_mult = (e && e[0] == '1') ? 1 : 2;
-  }
-  const int OB = outer_mult * NB;
+  const int OB = lu_outer_block();
   static int spec_default = -1;
   if (spec_default < 0) {
     const char* e = getenv("MMR_LU_SPEC");  // 0: always the pivoting strip kernels
@@ -1567,7 +1868,11 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
   const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
   const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256 * 256) : 0;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 4 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes);
+  // inverse stash: L11^-1 | U11^-1 of every panel, written into the diagonal blocks at the end if no panel was
+  // rejected (inverse format, see lu_sweep_kernel)
+  const int npanel_slots = 2 * (int)ceil_div64(N, OB);
+  const size_t stash_bytes = spec_on ? sizeof(double) * (size_t)npanel_slots * 2 * NB * NB : 0;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 4 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes + stash_bytes);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 256);
   if (rc) return rc;
@@ -1577,6 +1882,8 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   double* Lbuf = (double*)((char*)ctx->ws + 256 + scratch_bytes);
   void* d_spec = (char*)Lbuf + 4 * sizeof(double) * NB * NB;
   double* Sbuf = (double*)((char*)d_spec + spec_bytes);
+  double* stash = (double*)((char*)Sbuf + sbuf_bytes);
+  auto slot_of = [&](int kb) { return stash + (size_t)(2 * (kb / OB) + ((kb % OB) ? 1 : 0)) * 2 * NB * NB; };
   // inverse of the unit-lower diagonal block of inner panel `inner` of the outer block at kb
   auto Linv = [&](int kb, int inner) { return Lbuf + (size_t)((((kb / OB) & 1) << 1) + inner) * NB * NB; };
   MMR_CUDA(cudaMemsetAsync(d_info, 0, 2 * sizeof(int), ctx->stream));
@@ -1587,8 +1894,10 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   auto last_panel = [&](int kb) { return (min(OB, N - kb) > NB) ? kb + NB : kb; };
   // interchange records: slot(kb, inner), prepared once per panel on the stream that factored it
   auto pslot = [&](int kb, int inner) { return 2 + ((((kb / OB) & 1) << 1) + inner); };
+  // (speculative mode: a committed panel has identity pivots and a rejected one poisons its consumers, so
+  // the interchange kernels would be no-ops either way and are not launched at all)
   auto laswp = [&](cudaStream_t s, int cb, int ce, int slot0, int slot1, int dep) -> int {
-    if (ce <= cb) return 0;
+    if (ce <= cb || spec_on) return 0;
     const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, s);
     const int r = mmr_lu_laswp_apply(ctx, s, A, ld, cb, ce, slot0, slot1, d_fail, dep);
     mmr_prof_end(ctx, ps, 32.0 * NB * (double)(ce - cb), s);
@@ -1615,7 +1924,14 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   // panel [kb, kb+nb) and the inverse of its unit-lower diagonal block: speculative (diagonal pivots,
   // verified on the device, stream-ordered) or the pivoting strip kernels
   auto panel = [&](cudaStream_t s, int kb, int nb, double* Linv_out) -> int {
-    if (spec_on) return mmr_lu_panel_spec(ctx, s, A, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, d_fail);
+    if (spec_on) {
+      // U11^-1 goes straight into the panel's stash slot, L11^-1 is copied there behind the panel
+      double* slot = slot_of(kb);
+      const int r = mmr_lu_panel_spec(ctx, s, A, ld, N, kb, nb, d_ipiv, Sbuf, N - kb, Linv_out, slot + (size_t)NB * NB, d_fail, true);
+      if (r) return r;
+      MMR_CUDA(cudaMemcpyAsync(slot, Linv_out, sizeof(double) * nb * nb, cudaMemcpyDeviceToDevice, s));
+      return 0;
+    }
     const int r = mmr_lu_panel(ctx, s, A, ld, N, kb, nb, d_ipiv, d_info, scratch);
     if (r) return r;
     return mmr_lu_trtri(ctx, s, A + (int64_t)kb * ld + kb, ld, nb, Linv_out);
@@ -1628,8 +1944,9 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
     int r = 0;
     if (first_inner == 0) {
       if ((r = panel(s, kb, nb0, Linv(kb, 0)))) return r;
-      if ((r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, kb, kb + nb0, pslot(kb, 0), d_fail))) return r;
+      if (!spec_on && (r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, kb, kb + nb0, pslot(kb, 0), d_fail))) return r;
     }
+    if (first_inner != 0 && (r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, kb, kb + nb0, pslot(kb, 0), d_fail))) return r;
     if (ob <= NB) return 0;
     const int k1 = kb + NB, nb1 = ob - NB;
     if (first_inner == 0) {
@@ -1638,7 +1955,7 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
       if ((r = gemm(s, MMR_PROF_PANEL_GEMM, k1, N, kb, NB, k1, k1 + nb1, kb))) return r;
     }
     if ((r = panel(s, k1, nb1, Linv(kb, 1)))) return r;
-    if ((r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, k1, k1 + nb1, pslot(kb, 1), d_fail))) return r;
+    if (!spec_on && (r = mmr_lu_laswp_prepare(ctx, s, d_ipiv, k1, k1 + nb1, pslot(kb, 1), d_fail))) return r;
     return laswp(s, kb, k1, pslot(kb, 1), -1, k1);  // panel 1's interchanges on panel 0's columns
   };
   // trailing update of the column range [cb, ce) by the outer block [kb, kb+ob)
@@ -1702,9 +2019,17 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
     first_inner = (kf > kb0) ? 1 : 0;
     MMR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
   }
+  if (spec_on && h_info[0] == 0) {
+    // no panel was rejected: switch the factors to inverse format (diagonal panel blocks <- L11^-1 \ U11^-1)
+    lu_store_inverses_kernel<<<npanel_slots, 256, 0, ctx->stream>>>(A, ld, stash, npanel_slots, N, OB, 1, 0, d_fail);
+    MMR_CHECK_LAUNCH(ctx);
+    lu_set_format_kernel<<<1, 1, 0, ctx->stream>>>(d_ipiv, d_fail);
+    MMR_CHECK_LAUNCH(ctx);
+  }
   if (info_out) *info_out = h_info[0];
   return 0;
 }
+
 
 // U^T w = b (forward) then L^T v = w (backward), in place on d_b (length N).  Right-looking:
 // as soon as a diagonal block of the solution is final it is eliminated from ALL remaining
@@ -1757,6 +2082,8 @@ extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64
   int* h_perm = h_ipiv + N;
   MMR_CUDA(cudaMemcpyAsync(h_ipiv, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
   MMR_CUDA(cudaStreamSynchronize(ctx->stream));
+  const bool inv_format = (h_ipiv[0] & LU_FORMAT_INVDIAG) != 0;
+  h_ipiv[0] &= LU_IPIV_MASK;
   for (int i = 0; i < N; ++i) h_perm[i] = i;
   for (int i = N - 1; i >= 0; --i) {
     const int p = h_ipiv[i];
@@ -1774,7 +2101,8 @@ extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64
   for (int64_t j = 0; j < nrhs; ++j) {
     double* b = d_B + j * N64;
     const int pt = mmr_prof_begin(ctx, MMR_PROF_TRISOLVE, ctx->stream);
-    rc = mmr_lu_tri_solves(ctx, N, d_LU, ld, b);
+    rc = inv_format ? lu_sweeps_inv(ctx, ctx->stream, N, lu_outer_block(), 1, 0, d_LU, ld, N, b)
+                    : mmr_lu_tri_solves(ctx, N, d_LU, ld, b);
     if (rc) return rc;
     mmr_prof_end(ctx, pt, 8.0 * N * (double)N, ctx->stream);
     MMR_CUDA(cudaMemcpyAsync(d_tmp, b, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1794,8 +2122,6 @@ extern "C" int mmr_lu_solve(mmr_ctx* ctx, int64_t N64, const double* d_LU, int64
 // as the single-GPU path.  The triangular solves walk the panels in order with one nbw-double
 // broadcast per panel.
 // =======================================================================================
-#include "comm.h"
-
 namespace {
 
 // fold the guard word that arrived with a broadcast record into this rank's sticky guard
@@ -1884,14 +2210,18 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
   bool spec_on = spec_default != 0;
 
   // workspace: [info | strip scratch | spec scratch | 2 x broadcast record | spec panel]
-  // broadcast record of an outer block: header (L11^-1 of both panels, the block's pivots, the owner's
-  // speculation guard word) + packed panel (m x ob, ld = m): ONE ncclBroadcast per outer block.
+  // broadcast record of an outer block: the packed panel (m x ob, ld = m) followed by a header (L11^-1 of both
+  // panels, the block's pivots, the owner's speculation guard word).  In speculative mode the record IS the
+  // panel buffer of the factorization (nothing is packed), panel 0's columns travel while panel 1 is still
+  // being factored, and the copy into the matrix happens after the broadcast has been issued.
   const size_t scratch_bytes = (mmr_lu_panel_scratch_bytes() + 255) / 256 * 256;
   const size_t spec_bytes = (mmr_lu_spec_scratch_bytes() + 255) / 256 * 256;
   const size_t hdr_doubles = 2 * (size_t)NB * NB + NB + 2;  // 2 x L11^-1, 2*NB pivot ints, guard word (+ pad)
   const size_t rec_bytes = ((sizeof(double) * (hdr_doubles + (size_t)N * obw) + 255) / 256) * 256;
-  const size_t sbuf_bytes = spec_on ? ((sizeof(double) * (size_t)N * NB + 255) / 256) * 256 : 0;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + spec_bytes + 2 * rec_bytes + sbuf_bytes + 512);
+  // inverse stash of my panels (slot 2 * local block + inner: L11^-1 | U11^-1), see lu_sweep_kernel
+  const int npanel_slots = 2 * (int)ceil_div64(ncols_local, obw);
+  const size_t stash_bytes = spec_on ? ((sizeof(double) * (size_t)(npanel_slots + 2) * 2 * NB * NB + 255) / 256) * 256 : 0;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + spec_bytes + 2 * rec_bytes + stash_bytes + 512);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 2 * sizeof(int) * (size_t)N + 256);
   if (rc) return rc;
@@ -1903,14 +2233,22 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
   int* d_ipiv = d_ipiv_out;
   double* rec[2] = {(double*)(base + 256 + scratch_bytes + spec_bytes),
                     (double*)(base + 256 + scratch_bytes + spec_bytes + rec_bytes)};
-  double* Sbuf = (double*)(base + 256 + scratch_bytes + spec_bytes + 2 * rec_bytes);
-  auto LinvOf = [&](int s, int inner) { return rec[s & 1] + (size_t)inner * NB * NB; };
-  auto IpivOf = [&](int s) { return (int*)(rec[s & 1] + 2 * (size_t)NB * NB); };
-  auto FailOf = [&](int s) { return (int*)(rec[s & 1] + 2 * (size_t)NB * NB + NB); };
-  auto PanelOf = [&](int s) { return rec[s & 1] + hdr_doubles; };
+  double* stash = (double*)(base + 256 + scratch_bytes + spec_bytes + 2 * rec_bytes);
+  auto slot_of = [&](int s, int inner) { return stash + (size_t)(2 * (s / R) + inner) * 2 * NB * NB; };
+  auto Mrows = [&](int s) { return N - s * obw; };
+  auto Width = [&](int s) { return min(obw, N - s * obw); };
+  auto PanelOf = [&](int s) { return rec[s & 1]; };
+  auto HdrOf = [&](int s) { return rec[s & 1] + (size_t)Mrows(s) * Width(s); };
+  auto LinvOf = [&](int s, int inner) { return HdrOf(s) + (size_t)inner * NB * NB; };
+  auto IpivOf = [&](int s) { return (int*)(HdrOf(s) + 2 * (size_t)NB * NB); };
+  auto FailOf = [&](int s) { return (int*)(HdrOf(s) + 2 * (size_t)NB * NB + NB); };
   auto pslot = [&](int s, int inner) { return 2 + (((s & 1) << 1) + inner); };
   // start of the last panel of block s: what a consumer of the whole block depends on
-  auto last_panel = [&](int s) { return (min(obw, N - s * obw) > NB) ? s * obw + NB : s * obw; };
+  auto last_panel = [&](int s) { return (Width(s) > NB) ? s * obw + NB : s * obw; };
+  cudaStream_t cm = ctx->comm;
+  cudaEvent_t e_upd = ctx->evd[0], e_free = ctx->evd[1], e_pA = ctx->evd[2], e_pB = ctx->evd[3], e_start = ctx->evd[4],
+              e_end = ctx->evd[5];
+  cudaEvent_t e_rec[2] = {ctx->evd[6], ctx->evd[7]};
   MMR_CUDA(cudaMemsetAsync(d_info, 0, 2 * sizeof(int), st));
   double* Al = d_Qlocal;
 
@@ -1920,25 +2258,75 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
     mmr_prof_end(ctx, ps, 2.0 * nb * nb * (double)ncols, s_);
     return r;
   };
-  // panel of the owner's local storage `Ash` (global column c at Ash + c*ld) and its L11^-1
-  auto panel = [&](cudaStream_t s_, double* Ash, int kb, int nb, double* Linv_out) -> int {
-    if (spec_on) return mmr_lu_panel_spec(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, Sbuf, Linv_out, d_spec, d_fail);
-    const int r = mmr_lu_panel(ctx, s_, Ash, ld, N, kb, nb, d_ipiv, d_info, scratch);
-    if (r) return r;
-    return mmr_lu_trtri(ctx, s_, Ash + (int64_t)kb * ld + kb, ld, nb, Linv_out);
+  auto copy_guarded = [&](cudaStream_t s_, const double* src, int64_t lds_, int rows, int cols, double* dst, int64_t ldd,
+                          int dep) -> int {
+    if (rows <= 0 || cols <= 0) return 0;
+    const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)rows * cols, 256 * 8));
+    lu_copy_guarded_kernel<<<g, 256, 0, s_>>>(src, lds_, rows, cols, dst, ldd, d_fail, dep);
+    MMR_CHECK_LAUNCH(ctx);
+    return 0;
   };
-  // factor outer block s (owned by this rank) on stream `strm` and fill its broadcast record
-  // (first_inner = 1: resuming after a rejected panel 1 -- panel 0 is committed in A, its L11^-1 is rebuilt)
-  auto factor_and_pack = [&](int s, cudaStream_t strm, int first_inner) -> int {
-    const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
-    const int nb0 = min(NB, ob), nb1 = ob - nb0;
+  // split: panel 0's columns of the record are broadcast on their own as soon as they exist
+  auto split_bcast = [&](int s, int first_inner) { return R > 1 && spec_on && first_inner == 0 && Width(s) > NB; };
+
+  // Speculative factorization of my block s straight into its broadcast record (stream-ordered, no packing):
+  //   diag+inverses(0) -> L21(0) [+check]  => e_pA
+  //   U12 = L11^-1 A12 (into the record) -> A22 -= L21 U12 -> diag+inverses(1) -> L21(1) [+check] -> guard word  => e_pB
+  //   (after e_pB, off the chain) record -> matrix
+  auto factor_spec = [&](int s, cudaStream_t strm) -> int {
+    const int kb = s * obw, ob = Width(s), m = Mrows(s);
+    const int nb0 = min(NB, ob), nb1 = ob - nb0, k1 = kb + nb0;
     double* Ash = Al + ((int64_t)(s / R) * obw - kb) * ld;  // global column kb -> my local column
+    double* P = PanelOf(s);
+    lu_fill_ipiv_kernel<<<(unsigned)ceil_div64(ob, 256), 256, 0, strm>>>(IpivOf(s), d_ipiv + kb, kb, ob);
+    MMR_CHECK_LAUNCH(ctx);
+    // panel 0; U12 = L11^-1 A12 (out of place, into the record) shares the launch of L21 = A21 U11^-1
+    mmr_gemm::GemmAlt u12;
+    if (nb1 > 0) {
+      u12.m = nb0, u12.n = nb1, u12.k = nb0;
+      u12.A = LinvOf(s, 0), u12.lda = nb0;
+      u12.B = Ash + (int64_t)k1 * ld + kb, u12.ldb = ld;
+      u12.C = P + (size_t)nb0 * m, u12.ldc = m;
+    }
+    int r = mmr_lu_panel_spec(ctx, strm, Ash, ld, N, kb, nb0, d_ipiv, P, m, LinvOf(s, 0), slot_of(s, 0) + (size_t)NB * NB,
+                              d_fail, false, nb1 > 0 ? &u12 : nullptr);
+    if (r) return r;
+    if (split_bcast(s, 0)) MMR_CUDA(cudaEventRecord(e_pA, strm));
+    if (nb1 > 0) {
+      int ps = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, strm);
+      r = mmr_dgemm_launch(ctx, strm, N - k1, nb1, nb0, -1.0, P + nb0, m, P + (size_t)nb0 * m, m, 1.0,
+                           Ash + (int64_t)k1 * ld + k1, ld, d_fail, kb);
+      if (r) return r;
+      mmr_prof_end(ctx, ps, 2.0 * (N - k1) * (double)nb1 * nb0, strm);
+      r = mmr_lu_panel_spec(ctx, strm, Ash, ld, N, k1, nb1, d_ipiv, P + (size_t)nb0 * m + nb0, m, LinvOf(s, 1),
+                            slot_of(s, 1) + (size_t)NB * NB, d_fail, false);
+      if (r) return r;
+    }
+    MMR_CUDA(cudaMemcpyAsync(FailOf(s), d_fail, sizeof(int), cudaMemcpyDeviceToDevice, strm));
+    MMR_CUDA(cudaEventRecord(e_pB, strm));
+    // record -> matrix, per panel (a rejected panel 1 must leave panel 0 and its U12 block committed: the
+    // host resumes from panel 1 with the pivoting kernels); L11^-1 -> inverse stash
+    MMR_CUDA(cudaMemcpyAsync(slot_of(s, 0), LinvOf(s, 0), sizeof(double) * nb0 * nb0, cudaMemcpyDeviceToDevice, strm));
+    if (nb1 > 0)
+      MMR_CUDA(cudaMemcpyAsync(slot_of(s, 1), LinvOf(s, 1), sizeof(double) * nb1 * nb1, cudaMemcpyDeviceToDevice, strm));
+    if ((r = copy_guarded(strm, P, m, m, nb0, Ash + (int64_t)kb * ld + kb, ld, kb))) return r;
+    if (nb1 > 0) {
+      if ((r = copy_guarded(strm, P + (size_t)nb0 * m, m, nb0, nb1, Ash + (int64_t)k1 * ld + kb, ld, kb))) return r;
+      if ((r = copy_guarded(strm, P + (size_t)nb0 * m + nb0, m, m - nb0, nb1, Ash + (int64_t)k1 * ld + k1, ld, k1))) return r;
+    }
+    return 0;
+  };
+  // Pivoting factorization of my block s in place, then packed into its record
+  // (first_inner = 1: resuming after a rejected panel 1 -- panel 0 is committed in A, its L11^-1 is rebuilt)
+  auto factor_pivoting = [&](int s, cudaStream_t strm, int first_inner) -> int {
+    const int kb = s * obw, ob = Width(s), m = Mrows(s);
+    const int nb0 = min(NB, ob), nb1 = ob - nb0;
+    double* Ash = Al + ((int64_t)(s / R) * obw - kb) * ld;
     int r = 0;
     if (first_inner == 0) {
-      if ((r = panel(strm, Ash, kb, nb0, LinvOf(s, 0)))) return r;
-    } else if ((r = mmr_lu_trtri(ctx, strm, Ash + (int64_t)kb * ld + kb, ld, nb0, LinvOf(s, 0)))) {
-      return r;
+      if ((r = mmr_lu_panel(ctx, strm, Ash, ld, N, kb, nb0, d_ipiv, d_info, scratch))) return r;
     }
+    if ((r = mmr_lu_trtri(ctx, strm, Ash + (int64_t)kb * ld + kb, ld, nb0, LinvOf(s, 0)))) return r;
     if (nb1 > 0) {
       const int k1 = kb + nb0;
       if (first_inner == 0) {
@@ -1950,30 +2338,36 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
         if (r) return r;
         mmr_prof_end(ctx, pg, 2.0 * (N - k1) * (double)nb1 * nb0, strm);
       }
-      if ((r = panel(strm, Ash, k1, nb1, LinvOf(s, 1)))) return r;
+      if ((r = mmr_lu_panel(ctx, strm, Ash, ld, N, k1, nb1, d_ipiv, d_info, scratch))) return r;
+      if ((r = mmr_lu_trtri(ctx, strm, Ash + (int64_t)k1 * ld + k1, ld, nb1, LinvOf(s, 1)))) return r;
       if ((r = mmr_lu_laswp(ctx, strm, Ash, ld, k1, k1 + nb1, kb, k1, d_ipiv, d_fail))) return r;
     }
-    // (unconditional copies: after a rejected panel the record is garbage, but it carries the guard word and
-    // every consumer of it skips its stores)
     MMR_CUDA(cudaMemcpy2DAsync(PanelOf(s), sizeof(double) * m, Ash + (int64_t)kb * ld + kb, sizeof(double) * ld,
                                sizeof(double) * m, ob, cudaMemcpyDeviceToDevice, strm));
     MMR_CUDA(cudaMemcpyAsync(IpivOf(s), d_ipiv + kb, sizeof(int) * ob, cudaMemcpyDeviceToDevice, strm));
     MMR_CUDA(cudaMemcpyAsync(FailOf(s), d_fail, sizeof(int), cudaMemcpyDeviceToDevice, strm));
+    MMR_CUDA(cudaEventRecord(e_pB, strm));
     return 0;
+  };
+  auto factor_block = [&](int s, cudaStream_t strm, int first_inner) -> int {
+    return (spec_on && first_inner == 0) ? factor_spec(s, strm) : factor_pivoting(s, strm, first_inner);
   };
   // apply outer block s (interchanges, U12 in two 128-row steps, one rank-ob update) to my local
   // columns [c0, c1)
   auto update_local = [&](int s, int c0, int c1) -> int {
     if (c1 <= c0) return 0;
-    const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
+    const int kb = s * obw, ob = Width(s), m = Mrows(s);
     const int nb0 = min(NB, ob), nb1 = ob - nb0;
     const int dep = last_panel(s);
     const double* P = PanelOf(s);
     double* B = Al + (int64_t)c0 * ld + kb;
-    int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
-    int r = mmr_lu_laswp_apply(ctx, st, Al, ld, c0, c1, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1, d_fail, dep);
-    if (r) return r;
-    mmr_prof_end(ctx, ps, 32.0 * ob * (double)(c1 - c0), st);
+    int ps, r = 0;
+    if (!spec_on) {
+      ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
+      r = mmr_lu_laswp_apply(ctx, st, Al, ld, c0, c1, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1, d_fail, dep);
+      if (r) return r;
+      mmr_prof_end(ctx, ps, 32.0 * ob * (double)(c1 - c0), st);
+    }
     if ((r = trsm(st, LinvOf(s, 0), nb0, B, c1 - c0, dep))) return r;
     if (nb1 > 0) {
       ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
@@ -1990,44 +2384,58 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
     }
     return 0;
   };
-  // broadcast record s on the side stream (overlaps the main stream's update of block s-1), then fold the
-  // owner's guard word into mine; ev[2 + (s&1)] marks the arrival
-  auto bcast_record = [&](int s) -> int {
-    const int kb = s * obw, ob = min(obw, N - kb), m = N - kb;
+  // broadcast record s on the communication stream (beside the panel chain and the trailing update), then
+  // fold the owner's guard word into mine; e_rec[s & 1] marks the arrival.  `split`: panel 0's columns first.
+  auto bcast_record = [&](int s, bool split) -> int {
+    const int ob = Width(s), m = Mrows(s), owner = s % R;
+    const int nb0 = min(NB, ob);
     if (R > 1) {
-      const size_t bytes = sizeof(double) * (hdr_doubles + (size_t)m * ob);
-      const int pc = mmr_prof_begin(ctx, MMR_PROF_COMM, side);
-      const int r = mmr_comm_bcast_bytes(ctx, rec[s & 1], bytes, s % R, side);
+      const size_t all = sizeof(double) * ((size_t)m * ob + hdr_doubles);
+      const size_t part0 = split ? sizeof(double) * (size_t)m * nb0 : 0;
+      if (split) {
+        if (me == owner) MMR_CUDA(cudaStreamWaitEvent(cm, e_pA, 0));
+        const int pc = mmr_prof_begin(ctx, MMR_PROF_COMM, cm);
+        const int r = mmr_comm_bcast_bytes(ctx, PanelOf(s), part0, owner, cm);
+        if (r) return r;
+        mmr_prof_end(ctx, pc, (double)part0, cm);
+      }
+      if (me == owner) MMR_CUDA(cudaStreamWaitEvent(cm, e_pB, 0));
+      const int pc = mmr_prof_begin(ctx, MMR_PROF_COMM, cm);
+      const int r = mmr_comm_bcast_bytes(ctx, (char*)PanelOf(s) + part0, all - part0, owner, cm);
       if (r) return r;
-      mmr_prof_end(ctx, pc, (double)bytes, side);
+      mmr_prof_end(ctx, pc, (double)(all - part0), cm);
+    } else {
+      MMR_CUDA(cudaStreamWaitEvent(cm, e_pB, 0));
     }
-    lu_absorb_fail_kernel<<<1, 1, 0, side>>>(FailOf(s), d_fail);
+    lu_absorb_fail_kernel<<<1, 1, 0, cm>>>(FailOf(s), d_fail);
     MMR_CHECK_LAUNCH(ctx);
-    MMR_CUDA(cudaEventRecord(ctx->ev[2 + (s & 1)], side));
+    MMR_CUDA(cudaEventRecord(e_rec[s & 1], cm));
     return 0;
   };
 
   // One pass over the blocks from s0 on.  Entry state: every block before s0 is factored and applied
   // everywhere, block s0 has received all earlier updates (first_inner = 1: and its panel 0 is done).
   auto run = [&](int s0, int first_inner) -> int {
-    MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
-    MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));  // the side stream starts after everything queued so far
+    MMR_CUDA(cudaEventRecord(e_start, st));
+    MMR_CUDA(cudaStreamWaitEvent(side, e_start, 0));  // side and comm streams start after everything queued so far
+    MMR_CUDA(cudaStreamWaitEvent(cm, e_start, 0));
     int r = 0;
-    if (me == s0 % R && (r = factor_and_pack(s0, side, first_inner))) return r;
-    if ((r = bcast_record(s0))) return r;
+    if (me == s0 % R && (r = factor_block(s0, side, first_inner))) return r;
+    if ((r = bcast_record(s0, split_bcast(s0, first_inner)))) return r;
     for (int s = s0; s < S; ++s) {
       const int kb = s * obw;
-      const int ob = min(obw, N - kb);
+      const int ob = Width(s);
       const int nb0 = min(NB, ob), nb1 = ob - nb0;
-      MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[2 + (s & 1)], 0));
+      MMR_CUDA(cudaStreamWaitEvent(st, e_rec[s & 1], 0));
       // from here on the main stream no longer reads record s-1 = the buffer of record s+1
-      MMR_CUDA(cudaEventRecord(ctx->ev[1], st));
-      MMR_CUDA(cudaMemcpyAsync(d_ipiv + kb, IpivOf(s), sizeof(int) * ob, cudaMemcpyDeviceToDevice, st));
-      if ((r = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb, kb + nb0, pslot(s, 0), d_fail))) return r;
-      if (nb1 > 0 && (r = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb + nb0, kb + ob, pslot(s, 1), d_fail))) return r;
-      // my already-factored blocks (global index < s): interchanges only
-      const int nleft = (s > me) ? ((s - 1 - me) / R + 1) : 0;
-      {
+      MMR_CUDA(cudaEventRecord(e_free, st));
+      if (me != s % R)
+        MMR_CUDA(cudaMemcpyAsync(d_ipiv + kb, IpivOf(s), sizeof(int) * ob, cudaMemcpyDeviceToDevice, st));
+      if (!spec_on) {
+        if ((r = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb, kb + nb0, pslot(s, 0), d_fail))) return r;
+        if (nb1 > 0 && (r = mmr_lu_laswp_prepare(ctx, st, d_ipiv, kb + nb0, kb + ob, pslot(s, 1), d_fail))) return r;
+        // my already-factored blocks (global index < s): interchanges only
+        const int nleft = (s > me) ? ((s - 1 - me) / R + 1) : 0;
         const int ps = mmr_prof_begin(ctx, MMR_PROF_LASWP, st);
         r = mmr_lu_laswp_apply(ctx, st, Al, ld, 0, nleft * obw, pslot(s, 0), nb1 > 0 ? pslot(s, 1) : -1, d_fail,
                                last_panel(s));
@@ -2042,21 +2450,25 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
       if (own_next) {
         // look-ahead: bring my next block up to date first, then factor it on the side stream while
         // the main stream updates the rest of my trailing columns
-        const int ob1 = min(obw, N - (s + 1) * obw);
+        const int ob1 = Width(s + 1);
         if ((r = update_local(s, ct0, ct0 + ob1))) return r;
-        MMR_CUDA(cudaEventRecord(ctx->ev[0], st));
+        MMR_CUDA(cudaEventRecord(e_upd, st));
         if ((r = update_local(s, ct0 + ob1, ct1))) return r;
-        MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[0], 0));
-        if ((r = factor_and_pack(s + 1, side, 0))) return r;
+        MMR_CUDA(cudaStreamWaitEvent(side, e_upd, 0));  // (implies e_free: the record buffer of s+1 is free)
+        if ((r = factor_block(s + 1, side, 0))) return r;
       } else {
         if ((r = update_local(s, ct0, ct1))) return r;
-        MMR_CUDA(cudaStreamWaitEvent(side, ctx->ev[1], 0));
       }
-      if (have_next && (r = bcast_record(s + 1))) return r;
+      if (have_next) {
+        MMR_CUDA(cudaStreamWaitEvent(cm, e_free, 0));
+        if ((r = bcast_record(s + 1, split_bcast(s + 1, 0)))) return r;
+      }
     }
-    // whatever follows on the main stream comes after everything on the side stream
-    MMR_CUDA(cudaEventRecord(ctx->ev[0], side));
-    MMR_CUDA(cudaStreamWaitEvent(st, ctx->ev[0], 0));
+    // whatever follows on the main stream comes after everything on the other two streams
+    MMR_CUDA(cudaEventRecord(e_end, side));
+    MMR_CUDA(cudaStreamWaitEvent(st, e_end, 0));
+    MMR_CUDA(cudaEventRecord(e_end, cm));
+    MMR_CUDA(cudaStreamWaitEvent(st, e_end, 0));
     return 0;
   };
 
@@ -2075,6 +2487,16 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
     s0 = kf / obw;
     first_inner = (kf > s0 * obw) ? 1 : 0;
     MMR_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+  }
+  if (spec_on) {
+    // no panel was rejected anywhere (the guard word is the same on every rank): inverse format
+    if (npanel_slots > 0) {
+      lu_store_inverses_kernel<<<npanel_slots, 256, 0, st>>>(Al, ld, stash, npanel_slots, N, obw, R, me, d_fail);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+    lu_set_format_kernel<<<1, 1, 0, st>>>(d_ipiv, d_fail);
+    MMR_CHECK_LAUNCH(ctx);
+    MMR_CUDA(cudaStreamSynchronize(st));
   }
   if (info_out) *info_out = h_info[0];  // only the owner of a zero pivot sees it; callers reduce over ranks
   return 0;
@@ -2118,6 +2540,19 @@ extern "C" int mmr_lu_trisolve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_loc
   }
   int* d_perm = (int*)((char*)ctx->ws2 + off);
   double* d_tmp = (double*)((char*)ctx->ws2 + off + perm_bytes);
+  int* h_ipiv = (int*)ctx->hpin;
+  int* h_perm = h_ipiv + N;
+  MMR_CUDA(cudaMemcpyAsync(h_ipiv, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+  MMR_CUDA(cudaStreamSynchronize(st));
+  const bool inv_format = (h_ipiv[0] & LU_FORMAT_INVDIAG) != 0;
+  h_ipiv[0] &= LU_IPIV_MASK;
+  const int pt = mmr_prof_begin(ctx, MMR_PROF_TRISOLVE, st);
+  if (inv_format) {
+    int64_t mine = 0;
+    for (int s = me; s < S; s += R) mine += min(obw, N - s * obw);
+    rc = lu_sweeps_inv(ctx, st, N, obw, R, me, Al, ld, (int)mine, d_b);
+    if (rc) return rc;
+  } else {
 
   // ---- triangular solves, block by block (each block in two <= 128-row steps) -----------------
   const size_t diag_smem = (size_t)SB * (SB + 1) * sizeof(double);
@@ -2169,11 +2604,9 @@ extern "C" int mmr_lu_trisolve_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_loc
       if (rc) return rc;
     }
   }
+  }  // plain format
+  mmr_prof_end(ctx, pt, 8.0 * N * (double)nrows_local, st);
   // ---- x = P v (pivots are replicated) ------------------------------------------------------
-  int* h_ipiv = (int*)ctx->hpin;
-  int* h_perm = h_ipiv + N;
-  MMR_CUDA(cudaMemcpyAsync(h_ipiv, d_ipiv, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
-  MMR_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < N; ++i) h_perm[i] = i;
   for (int i = N - 1; i >= 0; --i) {
     const int p = h_ipiv[i];

@@ -314,8 +314,9 @@ def test_lu_solve_random_dense_vs_numpy(ctx, N):
     assert resid < 1e-14, resid
     cond = np.linalg.cond(Q)
     np.testing.assert_allclose(x, ref, rtol=0, atol=1e-13 * cond * np.abs(ref).max())
-    # pivots are a valid LAPACK-style sequence
+    # pivots are a valid LAPACK-style sequence (bit 30 of ipiv[0] is the factor-format flag)
     p = ipiv.cpu().numpy()
+    p[0] &= (1 << 30) - 1
     assert np.all(p >= np.arange(N)) and np.all(p < N)
 
 
@@ -339,10 +340,22 @@ def test_lu_speculative_panels_then_pivoting(ctx, N, ndom):
     resid = np.linalg.norm(Q @ x - b) / (np.linalg.norm(Q) * np.linalg.norm(x))
     assert resid < 1e-14, resid
     p = ipiv.cpu().numpy()
+    # bit 30 of ipiv[0]: "inverse format" -- set exactly when no panel needed an interchange; the diagonal
+    # panel blocks then hold L11^-1 \ U11^-1 (include/mmr_b200.h, mmr_lu_factor)
+    inv_format = bool(p[0] & (1 << 30))
+    p[0] &= (1 << 30) - 1
+    assert inv_format == (ndom == N)
     nfull = (ndom // 128) * 128 if ndom < N else N  # panels that lie entirely in the dominant part
     assert np.array_equal(p[:nfull], np.arange(nfull))
     # packed factors reproduce Q^T = P L U
-    LU = dQ[:, :N].cpu().numpy().T  # column-major view A = Q^T
+    LU = dQ[:, :N].cpu().numpy().T.copy()  # column-major view A = Q^T
+    if inv_format:
+        for kb in range(0, N, 128):
+            nb = min(128, N - kb)
+            D = LU[kb:kb + nb, kb:kb + nb]
+            L11 = np.linalg.inv(np.tril(D, -1) + np.eye(nb))
+            U11 = np.linalg.inv(np.triu(D))
+            LU[kb:kb + nb, kb:kb + nb] = np.tril(L11, -1) + U11
     L = np.tril(LU, -1) + np.eye(N)
     U = np.triu(LU)
     PA = Q.T.copy()
