@@ -223,6 +223,13 @@ int mmr_field_currents(mmr_ctx* ctx, int64_t m, const double* d_obs, int64_t nse
 int mmr_nccl_unique_id(void* id128_out);
 int mmr_comm_init(mmr_ctx* ctx, const void* id128, int nranks, int rank);
 int mmr_comm_destroy(mmr_ctx* ctx);
+/* Optional: peer-memory buffers for the flag-synchronised triangular sweeps of the distributed LU (CUDA IPC, one
+ * NVSwitch box).  Every rank exports the 64-byte handle of its buffer, the host gathers the handles of ranks
+ * 0..nranks-1 into one table (64 bytes each) and every rank opens it.  Without them the sweeps use one small
+ * ncclBroadcast per block. */
+int mmr_comm_p2p_export(mmr_ctx* ctx, void* handle64_out);
+int mmr_comm_p2p_open(mmr_ctx* ctx, const void* handles, int nranks, int rank);
+int mmr_comm_p2p_disable(mmr_ctx* ctx); /* back to the NCCL broadcasts (all ranks must agree) */
 
 /*
  * Distributed GMRES: this rank owns nrows_local rows of Q (row-major, ld >= N), the rows of the

@@ -121,6 +121,9 @@ _SIGNATURES = {
     "mmr_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "mmr_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "mmr_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "mmr_comm_p2p_disable": (ctypes.c_int, [ctypes.c_void_p]),
+    "mmr_comm_p2p_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "mmr_comm_p2p_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "mmr_gmres_dist": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64,
@@ -396,6 +399,24 @@ class Context:
         idbuf = ctypes.create_string_buffer(broadcast_bytes(bytes(idbuf), src=0), 128)
         _check(self.lib, self.lib.mmr_comm_init(self.handle, ctypes.cast(idbuf, ctypes.c_void_p), world, rank))
         self.nranks, self.rank = world, rank
+        # peer-memory buffers of the triangular sweeps (CUDA IPC): handles travel over torch.distributed
+        self.p2p = False
+        if world <= 16 and os.environ.get("MMR_P2P", "1") != "0":
+            mine = (ctypes.c_char * 64)()
+            ok = self.lib.mmr_comm_p2p_export(self.handle, ctypes.cast(mine, ctypes.c_void_p)) == 0
+            table = [None] * world
+            dist.all_gather_object(table, bytes(mine) if ok else None)
+            if all(h is not None for h in table):
+                blob = ctypes.create_string_buffer(b"".join(table), 64 * world)
+                ok = self.lib.mmr_comm_p2p_open(self.handle, ctypes.cast(blob, ctypes.c_void_p), world, rank) == 0
+            else:
+                ok = False
+            # every rank must take the same path
+            votes = [None] * world
+            dist.all_gather_object(votes, bool(ok))
+            self.p2p = all(votes)
+            if not self.p2p:
+                self.lib.mmr_comm_p2p_disable(self.handle)
 
     def gmres_dist(self, N, nrows_local, tgt_block, Qlocal, ld, b, x, tol=1e-10, restart=200, maxit=2000):
         iters = ctypes.c_int(0)

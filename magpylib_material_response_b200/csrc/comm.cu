@@ -95,8 +95,79 @@ extern "C" int mmr_comm_init(mmr_ctx* ctx, const void* id128, int nranks, int ra
   return 0;
 }
 
+// ---- peer-memory buffers (CUDA IPC) for the flag-synchronised triangular sweeps ----------------------------
+// Every rank allocates one buffer, exports its 64-byte IPC handle (mmr_comm_p2p_export), the host layer gathers
+// the handles of all ranks (torch.distributed is plumbing only) and hands the table to mmr_comm_p2p_open, which
+// maps every peer's buffer into this process.  All GPUs of one NVSwitch box reach each other directly.
+extern "C" int mmr_comm_p2p_export(mmr_ctx* ctx, void* handle64_out) {
+  MMR_ARG(ctx != nullptr && handle64_out != nullptr, "NULL ctx/handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceGuard g(ctx->device);
+  if (!ctx->p2p_local) {
+    MMR_CUDA(cudaMalloc(&ctx->p2p_local, mmr_p2p_bytes()));
+    MMR_CUDA(cudaMemset(ctx->p2p_local, 0, mmr_p2p_bytes()));
+  }
+  cudaIpcMemHandle_t h;
+  MMR_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+  memcpy(handle64_out, &h, 64);
+  return 0;
+}
+
+extern "C" int mmr_comm_p2p_open(mmr_ctx* ctx, const void* handles, int nranks, int rank) {
+  MMR_ARG(ctx != nullptr && handles != nullptr, "NULL ctx/handles");
+  MMR_ARG(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, "bad nranks/rank (at most 16 ranks)");
+  MMR_ARG(ctx->p2p_local != nullptr, "mmr_comm_p2p_export has not been called");
+  DeviceGuard g(ctx->device);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      ctx->p2p_peer[r] = ctx->p2p_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      mmr_set_error("cudaIpcOpenMemHandle for rank %d failed (%s); the triangular sweeps fall back to NCCL broadcasts",
+                    r, cudaGetErrorString(e));
+      ctx->p2p_ready = false;
+      return 1000 + (int)e;
+    }
+    ctx->p2p_peer[r] = ptr;
+  }
+  if (!ctx->p2p_dev_table) MMR_CUDA(cudaMalloc((void**)&ctx->p2p_dev_table, sizeof(void*) * 16));
+  MMR_CUDA(cudaMemcpy(ctx->p2p_dev_table, ctx->p2p_peer, sizeof(void*) * 16, cudaMemcpyHostToDevice));
+  ctx->p2p_ready = true;
+  ctx->p2p_epoch = 0;
+  return 0;
+}
+
+extern "C" int mmr_comm_p2p_disable(mmr_ctx* ctx) {
+  if (ctx) ctx->p2p_ready = false;
+  return 0;
+}
+
+static void p2p_release(mmr_ctx* ctx) {
+  for (int r = 0; r < 16; ++r) {
+    if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_local) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    ctx->p2p_peer[r] = nullptr;
+  }
+  if (ctx->p2p_dev_table) cudaFree(ctx->p2p_dev_table);
+  if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+  ctx->p2p_dev_table = nullptr;
+  ctx->p2p_local = nullptr;
+  ctx->p2p_ready = false;
+  cudaGetLastError();
+}
+
 extern "C" int mmr_comm_destroy(mmr_ctx* ctx) {
-  if (!ctx || !ctx->nccl_comm) return 0;
+  if (!ctx) return 0;
+  {
+    DeviceGuard g0(ctx->device);
+    p2p_release(ctx);
+  }
+  if (!ctx->nccl_comm) return 0;
   DeviceGuard g(ctx->device);
   g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
   ctx->nccl_comm = nullptr;

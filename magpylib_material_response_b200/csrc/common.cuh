@@ -33,6 +33,14 @@ struct mmr_ctx {
   void* nccl_comm = nullptr;
   int nranks = 1;
   int rank = 0;
+  // peer-memory exchange buffers of the multi-GPU triangular sweeps (comm.cu: mmr_comm_p2p_*): one buffer per
+  // rank, cudaMalloc'ed by its owner and opened by every peer through CUDA IPC.  Layout of a buffer:
+  // [2 x P2P_CAP doubles (forward / backward solution blocks) | P2P_FLAGS ints (epoch of every block)]
+  void* p2p_local = nullptr;        // my buffer
+  void* p2p_peer[16] = {nullptr};   // every rank's buffer as seen from this device ([rank] = p2p_local)
+  void** p2p_dev_table = nullptr;   // device copy of p2p_peer
+  bool p2p_ready = false;
+  int p2p_epoch = 0;
   // optional profiling records (mmr_ctx_set_profiling)
   bool profiling = false;
   struct ProfRec {
@@ -104,5 +112,9 @@ int mmr_func_smem(mmr_ctx* ctx, const void* func, size_t bytes);
 // profiling scope: records an event pair around the launches enqueued in between
 int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s);
 void mmr_prof_end(mmr_ctx* ctx, int idx, double units, cudaStream_t s);
+
+constexpr int64_t MMR_P2P_CAP = 1 << 18;  // doubles per direction (N <= 262144)
+constexpr int MMR_P2P_FLAGS = 4096;       // blocks per sweep
+static inline size_t mmr_p2p_bytes() { return sizeof(double) * 2 * MMR_P2P_CAP + sizeof(int) * 2 * MMR_P2P_FLAGS; }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

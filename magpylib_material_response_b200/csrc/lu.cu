@@ -1652,29 +1652,70 @@ __global__ void lu_set_format_kernel(int* __restrict__ ipiv, const int* __restri
 // at local column (t / R) * obw + c % obw of the owner t % R; rows are global.
 //   s_done : block whose piece of b is final (-1: none)      s_next : block CTA 0 finishes now (-1: none; owned)
 //   [far_lo, far_hi) : my local columns that receive the update by block s_done (CTAs 1..)
+//   peers  : NULL, or the table of every rank's exchange buffer (mmr_comm_p2p_*): finished blocks travel as
+//            direct stores into all peers' buffers + one flag word per block (value = `epoch` of this sweep)
+//            instead of an ncclBroadcast; a consumer spins on its own copy of the flag.  *p2p_err is set if a
+//            flag does not arrive within ~2 s (a peer died): the sweep then finishes with garbage, never hangs.
+constexpr int SWEEP_THREADS = 1024, SWEEP_WARPS = SWEEP_THREADS / 32, SWEEP_NC = 2 * NB / SWEEP_WARPS;
 template <bool FWD>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SWEEP_THREADS)
     lu_sweep_kernel(const double* __restrict__ Al, int64_t ld, int N, int obw, int R, int me, int s_done, int s_next,
-                    int far_lo, int far_hi, double* __restrict__ b) {
+                    int far_lo, int far_hi, double* __restrict__ b, void* const* __restrict__ peers, int epoch,
+                    int* __restrict__ p2p_err, long long* __restrict__ clk) {
   __shared__ double xs[2 * NB], ys[2 * NB], zs[2 * NB];
+  int nclk = 0;
+#define SWEEP_STAMP()                                                       \
+  do {                                                                      \
+    if (clk && threadIdx.x == 0 && nclk < 16) clk[blockIdx.x == 0 ? nclk : 16 + nclk] = clock64(); \
+    ++nclk;                                                                 \
+  } while (0)
+  SWEEP_STAMP();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u0 = s_done >= 0 ? s_done * obw : 0;
   const int nu = s_done >= 0 ? min(obw, N - u0) : 0;
+  const double* xsrc = b;  // where the finished block s_done is read from
+  if (peers) {
+    double* mine = (double*)peers[me];
+    xsrc = mine + (FWD ? 0 : MMR_P2P_CAP);
+    if (s_done >= 0 && s_done % R != me) {
+      if (tid == 0) {
+        const volatile int* flag = (const volatile int*)(mine + 2 * MMR_P2P_CAP) + (FWD ? 0 : MMR_P2P_FLAGS) + s_done;
+        const long long t0 = clock64();
+        while (*flag != epoch) {
+          if (clock64() - t0 > (1LL << 32)) {
+            atomicExch(p2p_err, 1);
+            break;
+          }
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+  }
   if (blockIdx.x != 0) {
     // far columns: a warp takes four columns per pass -- 32 independent loads per lane in flight before the
     // first reduction (one column per short-lived warp kept the memory pipeline at ~10 % of its bandwidth)
-    const int nwarps = (gridDim.x - 1) * 32;
-    for (int base = far_lo + 4 * ((blockIdx.x - 1) * 32 + warp); base < far_hi; base += 4 * nwarps) {
+    const int nwarps = (gridDim.x - 1) * SWEEP_WARPS;
+    for (int base = far_lo + 4 * ((blockIdx.x - 1) * SWEEP_WARPS + warp); base < far_hi; base += 4 * nwarps) {
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      // unconditional loads from clamped addresses, sixteen issued before the first use (see `dots` below)
+      const double* cp[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int i = lane + 32 * t;
-        if (i < nu) {
-          const double xv = b[u0 + i];
+      for (int c = 0; c < 4; ++c) cp[c] = Al + (int64_t)min(base + c, far_hi - 1) * ld + u0;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (base + c < far_hi) acc[c] = fma(Al[(int64_t)(base + c) * ld + u0 + i], xv, acc[c]);
+      for (int t = 0; t < 8; t += 4) {
+        double a16[4][4], xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = min(lane + 32 * (t + q), nu - 1);
+          xv[q] = (lane + 32 * (t + q) < nu) ? xsrc[u0 + i] : 0.0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a16[q][c] = __ldg(cp[c] + i);
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[c] = fma(a16[q][c], xv[q], acc[c]);
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1)
@@ -1687,95 +1728,145 @@ __global__ void __launch_bounds__(1024)
         if (g < N) b[g] -= a;
       }
     }
+    if (blockIdx.x == 1) SWEEP_STAMP();
     return;
   }
   if (s_next < 0) return;
   const int d0 = s_next * obw;
   const int nd = min(obw, N - d0), na = min(NB, nd);
   const double* blk = Al + (int64_t)((s_next / R) * obw) * ld;  // local column of global column d0
-  for (int i = tid; i < nu; i += blockDim.x) xs[i] = b[u0 + i];
+  SWEEP_STAMP();  // 1: prefetches issued, flag seen
+  for (int i = tid; i < nu; i += blockDim.x) xs[i] = xsrc[u0 + i];
   __syncthreads();
-  // Warp w owns the columns j = w + 32 c, c < 8, of the block.  A product phase is latency bound (a handful of
+  SWEEP_STAMP();  // 2: x staged
+  // Warp w owns the columns j = w + SWEEP_WARPS c, c < SWEEP_NC, of the block.  A product phase is latency bound (a handful of
   // DRAM round trips), so every lane first issues the loads of ALL eight columns and only then reduces: one
   // memory latency per phase instead of one per column.
   //   sums[c] = sum_{r in [lo(j), hi(j))} A[row0 + r, d0 + j] * v[r]
-  auto dots = [&](int row0, auto lo_of, auto hi_of, const double* v, double (&sums)[8]) {
-    double acc[8];
+  auto dots = [&](int row0, int nrow, auto lo_of, auto hi_of, const double* v, double (&sums)[SWEEP_NC]) {
+    double acc[SWEEP_NC];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int c = 0; c < SWEEP_NC; ++c) acc[c] = 0.0;
+    if (nrow > 0) {
+      const int64_t cstride = (int64_t)SWEEP_WARPS * ld;
+      // The loads are UNCONDITIONAL (rows / columns out of range read a clamped, valid address and are masked
+      // afterwards) and eight of them are issued before the first use: with predicated load -> fma pairs the
+      // in-order issue serialised them, one L2 round trip (~400 cycles) per load, 25 000 cycles per phase.
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int r = lane + 32 * t;
-      const double vr = v[r];  // (v has 256 readable entries; out-of-range rows are masked below)
+      for (int t = 0; t < 8; ++t) {
+        const int r = lane + 32 * t;
+        const double vr = v[r];  // (v has 256 readable entries)
+        const double* rowp = blk + row0 + min(r, nrow - 1);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int j = warp + 32 * c;
-        if (j < nd && r >= lo_of(j) && r < hi_of(j)) acc[c] = fma(blk[(int64_t)j * ld + row0 + r], vr, acc[c]);
+        for (int h = 0; h < SWEEP_NC; h += 8) {
+          double a8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a8[c] = __ldg(rowp + (int64_t)min(warp + SWEEP_WARPS * (h + c), nd - 1) * ld);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int j = warp + SWEEP_WARPS * (h + c);
+            const bool ok = j < nd && r >= lo_of(j) && r < hi_of(j);
+            acc[h + c] = fma(ok ? a8[c] : 0.0, vr, acc[h + c]);
+          }
+        }
       }
+      (void)cstride;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int c = 0; c < SWEEP_NC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) sums[c] = acc[c];
+    for (int c = 0; c < SWEEP_NC; ++c) sums[c] = acc[c];
   };
-  double sm[8];
+  double sm[SWEEP_NC];
   // (1) the update by block s_done
-  dots(u0, [&](int) { return 0; }, [&](int) { return nu; }, xs, sm);
+  dots(u0, nu, [&](int) { return 0; }, [&](int) { return nu; }, xs, sm);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int j = warp + 32 * c;
+  for (int c = 0; c < SWEEP_NC; ++c) {
+    const int j = warp + SWEEP_WARPS * c;
     if (lane == 0 && j < nd) ys[j] = b[d0 + j] - sm[c];
   }
   __syncthreads();
+  SWEEP_STAMP();  // 3: update by s_done
   // (2) the block itself: two panels a = [0, na), q = [na, nd) with inverted diagonal blocks
   if (FWD) {
     // w_a = U_aa^-T y_a   and, for the columns of q, the part of U_qq^-T y_q ... no: y_q is not final yet
-    dots(d0, [&](int) { return 0; }, [&](int j) { return j < na ? j + 1 : 0; }, ys, sm);
+    dots(d0, nd, [&](int) { return 0; }, [&](int j) { return j < na ? j + 1 : 0; }, ys, sm);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 32 * c;
+    for (int c = 0; c < SWEEP_NC; ++c) {
+      const int j = warp + SWEEP_WARPS * c;
       if (lane == 0 && j < na) zs[j] = sm[c];
     }
     __syncthreads();
-    dots(d0, [&](int) { return 0; }, [&](int j) { return j >= na ? na : 0; }, zs, sm);  // y_q -= U_aq^T w_a
+    dots(d0, nd, [&](int) { return 0; }, [&](int j) { return j >= na ? na : 0; }, zs, sm);  // y_q -= U_aq^T w_a
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 32 * c;
+    for (int c = 0; c < SWEEP_NC; ++c) {
+      const int j = warp + SWEEP_WARPS * c;
       if (lane == 0 && j >= na && j < nd) ys[j] -= sm[c];
     }
     __syncthreads();
-    dots(d0, [&](int) { return na; }, [&](int j) { return j >= na ? j + 1 : 0; }, ys, sm);  // w_q = U_qq^-T y_q
+    dots(d0, nd, [&](int) { return na; }, [&](int j) { return j >= na ? j + 1 : 0; }, ys, sm);  // w_q = U_qq^-T y_q
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 32 * c;
+    for (int c = 0; c < SWEEP_NC; ++c) {
+      const int j = warp + SWEEP_WARPS * c;
       if (lane == 0 && j >= na && j < nd) zs[j] = sm[c];
     }
   } else {
-    dots(d0, [&](int j) { return j + 1; }, [&](int j) { return j >= na ? nd : 0; }, ys, sm);  // v_q = L_qq^-T y_q
+    dots(d0, nd, [&](int j) { return j + 1; }, [&](int j) { return j >= na ? nd : 0; }, ys, sm);  // v_q = L_qq^-T y_q
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 32 * c;
+    for (int c = 0; c < SWEEP_NC; ++c) {
+      const int j = warp + SWEEP_WARPS * c;
       if (lane == 0 && j >= na && j < nd) zs[j] = ys[j] + sm[c];
     }
     __syncthreads();
-    dots(d0, [&](int) { return na; }, [&](int j) { return j < na ? nd : 0; }, zs, sm);  // y_a -= L_qa^T v_q
+    dots(d0, nd, [&](int) { return na; }, [&](int j) { return j < na ? nd : 0; }, zs, sm);  // y_a -= L_qa^T v_q
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 32 * c;
+    for (int c = 0; c < SWEEP_NC; ++c) {
+      const int j = warp + SWEEP_WARPS * c;
       if (lane == 0 && j < na) ys[j] -= sm[c];
     }
     __syncthreads();
-    dots(d0, [&](int j) { return j + 1; }, [&](int j) { return j < na ? na : 0; }, ys, sm);  // v_a = L_aa^-T y_a
+    dots(d0, nd, [&](int j) { return j + 1; }, [&](int j) { return j < na ? na : 0; }, ys, sm);  // v_a = L_aa^-T y_a
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 32 * c;
+    for (int c = 0; c < SWEEP_NC; ++c) {
+      const int j = warp + SWEEP_WARPS * c;
       if (lane == 0 && j < na) zs[j] = ys[j] + sm[c];
     }
   }
   __syncthreads();
+  SWEEP_STAMP();  // 4: both panels
   for (int j = tid; j < nd; j += blockDim.x) b[d0 + j] = zs[j];
+  if (peers) {
+    // publish the finished block: data into every rank's buffer (mine included), then the flags
+    for (int e = tid; e < R * nd; e += blockDim.x) {
+      const int r = e / nd, j = e - r * nd;
+      ((double*)peers[r] + (FWD ? 0 : MMR_P2P_CAP))[d0 + j] = zs[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < R) {
+      volatile int* flag = (volatile int*)((double*)peers[tid] + 2 * MMR_P2P_CAP) + (FWD ? 0 : MMR_P2P_FLAGS) + s_next;
+      *flag = epoch;
+    }
+  }
+  SWEEP_STAMP();  // 5: published
+#undef SWEEP_STAMP
+}
+
+// every block flag of a sweep has reached this rank (value == epoch); gives up after ~2 s
+__global__ void lu_p2p_wait_all_kernel(const int* flags, int S, int epoch, int* __restrict__ err) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S) return;
+  const volatile int* f = flags + t;
+  const long long t0 = clock64();
+  while (*f != epoch) {
+    if (clock64() - t0 > (1LL << 32)) {
+      atomicExch(err, 1);
+      break;
+    }
+  }
+  __threadfence_system();
 }
 
 }  // namespace
@@ -1786,7 +1877,21 @@ __global__ void __launch_bounds__(1024)
 static int lu_sweeps_inv(mmr_ctx* ctx, cudaStream_t st, int N, int obw, int R, int me, const double* Al, int64_t ld,
                          int ncols_local, double* d_b) {
   const int S = (int)ceil_div64(N, obw);
+  // peer-memory exchange (one NVSwitch box, mmr_comm_p2p_*) instead of one ncclBroadcast per block
+  const bool p2p = R > 1 && ctx->p2p_ready && N <= MMR_P2P_CAP && S <= MMR_P2P_FLAGS;
+  void* const* peers = p2p ? (void* const*)ctx->p2p_dev_table : nullptr;
+  int epoch = 0;
+  if (p2p) {
+    const int rcw = mmr_ws_reserve(ctx, 256);
+    if (rcw) return rcw;
+  }
+  int* p2p_err = (int*)ctx->ws + 2;  // (ws[0..1]: info / guard words of the factorization)
+  if (p2p) {
+    MMR_CUDA(cudaMemsetAsync(p2p_err, 0, sizeof(int), st));
+    epoch = ++ctx->p2p_epoch;
+  }
   auto step = [&](bool fwd, int s_done, int s_next_global) -> int {
+    long long* clk = nullptr;
     // my columns that receive the update by s_done, and whether I finish s_next
     const bool own_next = s_next_global >= 0 && s_next_global % R == me;
     int far_lo = 0, far_hi = 0;
@@ -1803,19 +1908,19 @@ static int lu_sweeps_inv(mmr_ctx* ctx, cudaStream_t st, int N, int obw, int R, i
     }
     const int nfar = std::max(0, far_hi - far_lo);
     if (!own_next && nfar == 0) return 0;
-    // CTA 0 + up to one far CTA per remaining SM (32 warps x 4 columns per pass each)
-    const unsigned grid = 1 + (unsigned)std::min<int64_t>(ctx->sm_count - 1, ceil_div64(nfar, 128));
+    // CTA 0 + up to one far CTA per remaining SM (4 columns per warp and pass)
+    const unsigned grid = 1 + (unsigned)std::min<int64_t>(ctx->sm_count - 1, ceil_div64(nfar, 4 * SWEEP_WARPS));
     if (fwd)
-      lu_sweep_kernel<true><<<grid, 1024, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
-                                                  far_hi, d_b);
+      lu_sweep_kernel<true><<<grid, SWEEP_THREADS, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
+                                                  far_hi, d_b, peers, epoch, p2p_err, clk);
     else
-      lu_sweep_kernel<false><<<grid, 1024, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
-                                                   far_hi, d_b);
+      lu_sweep_kernel<false><<<grid, SWEEP_THREADS, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
+                                                   far_hi, d_b, peers, epoch, p2p_err, clk);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   };
   auto bcast = [&](int s) -> int {
-    if (R <= 1) return 0;
+    if (R <= 1 || p2p) return 0;
     const int kb = s * obw, ob = std::min(obw, N - kb);
     const int pc = mmr_prof_begin(ctx, MMR_PROF_COMM, st);
     const int r = mmr_comm_bcast_bytes(ctx, d_b + kb, sizeof(double) * ob, s % R, st);
@@ -1826,9 +1931,27 @@ static int lu_sweeps_inv(mmr_ctx* ctx, cudaStream_t st, int N, int obw, int R, i
   if ((rc = step(true, -1, 0)) || (rc = bcast(0))) return rc;
   for (int s = 0; s + 1 < S; ++s)
     if ((rc = step(true, s, s + 1)) || (rc = bcast(s + 1))) return rc;
+  if (p2p) epoch = ++ctx->p2p_epoch;
   if ((rc = step(false, -1, S - 1)) || (rc = bcast(S - 1))) return rc;
   for (int s = S - 1; s >= 1; --s)
     if ((rc = step(false, s, s - 1)) || (rc = bcast(s - 1))) return rc;
+  if (p2p) {
+    // the solution is complete in my exchange buffer once the flags of ALL blocks are here (they come from
+    // different peers: the flag of block 0 says nothing about the data of block 1); then buffer -> d_b
+    lu_p2p_wait_all_kernel<<<(unsigned)ceil_div64(S, 256), 256, 0, st>>>(
+        (const int*)((double*)ctx->p2p_local + 2 * MMR_P2P_CAP) + MMR_P2P_FLAGS, S, epoch, p2p_err);
+    MMR_CHECK_LAUNCH(ctx);
+    MMR_CUDA(cudaMemcpyAsync(d_b, (double*)ctx->p2p_local + MMR_P2P_CAP, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+    // (the callers keep the pivots and the permutation in the first 2 N ints of the pinned buffer and reserve
+    // 256 bytes more)
+    int* h_err = (int*)((char*)ctx->hpin + 2 * sizeof(int) * (size_t)N + 128);
+    MMR_CUDA(cudaMemcpyAsync(h_err, p2p_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MMR_CUDA(cudaStreamSynchronize(st));
+    if (*h_err) {
+      mmr_set_error("peer-memory sweep: a block flag did not arrive within the time-out (a peer rank failed?)");
+      return -7;
+    }
+  }
   return 0;
 }
 
