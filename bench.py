@@ -24,7 +24,7 @@ entries) and solve Q x = J0 + chi*H_ext.  Headline unit: T-entries per second of
 --impl reference times the reference's own CPU algorithm (oracle port: magpylib is not installable here,
 see DESIGN.md) on the host cores for the same metric and config: ONE full-size step is always taken
 (recorded in cpu_baseline.full_size with its stage times); the W + K steps run at full size when that fits
-the time budget (MMR_REF_BUDGET_S, default 540 s), otherwise on the largest sample of the workload that does.
+the time budget (MMR_REF_BUDGET_S, default 420 s), otherwise on the largest sample of the workload that does.
 """
 
 from __future__ import annotations
@@ -107,7 +107,7 @@ def make_workload(name):
         return dict(
             pos=np.vstack([p1, p2]), quat=np.vstack([q1, q2]), dim=np.vstack([d1, d2]),
             pol=np.vstack([np.tile((0, 0, 1.0), (m, 1)), np.zeros((m, 3))]),
-            chi=np.vstack([np.full((m, 3), 0.5), np.full((m, 3), 1000.0)]), H_ext=np.zeros((2 * m, 3)),
+            chi=np.vstack([np.full((m, 3), 0.5), np.full((m, 3), 1000.0)]), H_ext=np.zeros((2 * m, 3)), groups=[m, m],
             desc=f"hard magnet chi=0.5 + soft-iron cube chi=1000 rotated 45deg, 2 x {nnn[0]}x{nnn[1]}x{nnn[2]} = {2 * m} cells",
         )
     if name.startswith("soft_cube_"):
@@ -314,7 +314,7 @@ def run_reference(args):
     name = args.workload or default_workload(args.gpus)
     w_full = make_workload(name)
     n_full = len(w_full["pos"])
-    budget = float(os.environ.get("MMR_REF_BUDGET_S", "540"))
+    budget = float(os.environ.get("MMR_REF_BUDGET_S", "420"))
     total = args.steps + args.warmup
     t_begin = time.perf_counter()
 
@@ -566,6 +566,9 @@ def run_ours(args):
     ipiv = ctx.empty(N, dtype=torch.int32)
     d_x = ctx.empty(N)
     solver = args.solver
+    from magpylib_material_response_b200.demag import _precond_blocks
+
+    bj_blocks = _precond_blocks(w.get("groups"), w["chi"]) if (solver == "gmres" and world == 1) else None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=ctx.device) if 8.0 * N * N < 0.5e9 else None
 
     def step():
@@ -581,6 +584,8 @@ def run_ours(args):
                 ctx.lu_solve(Q, ld, ipiv, d_x)
                 return None
             d_x.zero_()
+            if bj_blocks:
+                return ctx.gmres_bj(Q, ld, d_rhs, d_x, bj_blocks, tol=args.tol, restart=args.restart, maxit=5000)
             return ctx.gmres(Q, ld, d_rhs, d_x, tol=args.tol, restart=args.restart, maxit=5000)
         if solver == "lu":
             info = ctx.lu_solve_dist(N, 3 * n_local, tgt_block, Q, ld, d_x)
@@ -652,7 +657,8 @@ def run_ours(args):
     d2h = 8 * N * world
     if not args.no_e2e:
         kw = dict(solver=solver, tol=args.tol)
-        t_arr, xs = time_calls(lambda: apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"], **kw))
+        t_arr, xs = time_calls(lambda: apply_demag_arrays(w["pos"], w["quat"], w["dim"], w["pol"], w["chi"], w["H_ext"],
+                                                          groups=w.get("groups"), **kw))
         e2e_arrays = {"value": 9.0 * n * n / t_arr, "unit": "T-entries/s", "seconds_per_step": t_arr, "steps": args.steps,
                       "api": "magpylib_material_response_b200.demag.apply_demag_arrays (host numpy in/out)",
                       "max_abs_diff_vs_device_path": float(np.abs(rot.apply(xs) - x_dev).max())}
@@ -684,7 +690,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    tpath = ROOT / "profiles" / "ncu_traffic_r1.json"
+    tpath = ROOT / "profiles" / "ncu_traffic_r2.json"
     traffic = json.loads(tpath.read_text()) if tpath.exists() else {}
     asm_ms, asm_pairs, asm_cnt = prof["assemble"]
     gemm_ms, gemm_flops, gemm_cnt = prof["gemm"]
@@ -694,10 +700,10 @@ def run_ours(args):
     roof_asm = {"bound": "fp64", "achieved": asm_pairs * fpp / (asm_ms * 1e-3) / 1e12 if asm_ms else None,
                 "peak": peaks["fp64_fma_tflops"], "unit": "TFLOP/s (flop-equivalents of the reference algorithm, SURVEY 8d convention)",
                 "frac": ncu_pipe, "frac_src": "ncu sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of this kernel "
-                                              "(profiles/, see ncu_traffic_r1.json); NOT achieved/peak: the far-field path evaluates "
+                                              "(profiles/, see ncu_traffic_r2.json); NOT achieved/peak: the far-field path evaluates "
                                               "3 atan2 + 3 log per pair where the reference algorithm counts 24 + 6",
                 "traffic": traffic.get("assemble_cell_major", {}).get("ratio", 0) * 72.0 * asm_pairs / max(1, asm_cnt) or None,
-                "traffic_src": "72 B/pair x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
+                "traffic_src": "72 B/pair x ncu dram/algorithmic ratio (profiles/ncu_traffic_r2.json)",
                 "kernel": "assemble_cell_major_kernel", "ms_per_launch": asm_ms / max(1, asm_cnt),
                 "entries_per_s": 9.0 * asm_pairs / (asm_ms * 1e-3) if asm_ms else None, "peak_src": peaks["fp64_src"]}
     k_update = 256 if world == 1 else 3 * tgt_block  # rank of the trailing updates (two 128-column panels / one ownership block)
@@ -706,7 +712,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["fp64_dmma_tflops"],
                     "traffic": traffic.get("dgemm_nn", {}).get("ratio", 0) * (gemm_flops * 8.0 / k_update) / gemm_cnt or None,
-                    "traffic_src": f"C read+write bytes (16 B per C element = flops*8/k, rank-{k_update} updates) x ncu dram/algorithmic ratio (profiles/ncu_traffic_r1.json)",
+                    "traffic_src": f"C read+write bytes (16 B per C element = flops*8/k, rank-{k_update} updates) x ncu dram/algorithmic ratio (profiles/ncu_traffic_r2.json)",
                     "kernel": "LU trailing update (DMMA.8x8x4 GEMM)",
                     "launches": gemm_cnt, "ms_per_launch": gemm_ms / gemm_cnt,
                     "peak_src": "FP64 DMMA peak: " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry"}
@@ -735,7 +741,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "config": bench_config(name, w, solver),
         "sharding": {"row_block_cells": tgt_block, "ranks": world, "scheme": "block-cyclic target-row blocks" if world > 1 else "single GPU"},
-        "gmres": {"iters": gm[0], "relres": gm[1]} if gm else None,
+        "gmres": {"iters": gm[0], "relres": gm[1], "block_jacobi_blocks": bj_blocks} if gm else None,
         "roofline": roofline,
         "clocks": clocks,
         "stages": stages,

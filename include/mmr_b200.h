@@ -188,11 +188,20 @@ int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, co
  * Solves Q x = b (row-major Q, ld).  x holds the initial guess on entry.  Stops when the TRUE
  * residual ||b - Q x|| / ||b|| (recomputed at every restart = the iterative-refinement
  * check) <= tol, or after maxit matvecs.  iters_out / relres_out are host pointers.
- * Returns 0 on convergence, -4 if maxit was reached.
+ * Returns 0 on convergence, -4 if maxit was reached or the true residual stagnated above tol for two
+ * consecutive restart cycles (relres_out then holds the residual that was reached).
  */
 int mmr_gmres(mmr_ctx* ctx, int64_t N, const double* d_Q, int64_t ld, const double* d_b,
               double* d_x, double tol, int restart, int maxit, int* iters_out,
               double* relres_out);
+
+/* GMRES with a block-Jacobi right preconditioner: the diagonal blocks Q[r0:r0+rows, r0:r0+rows] of the `nblocks`
+ * listed row ranges (host arrays; one magnet of a multi-magnet collection each, typically only the
+ * high-susceptibility ones) are copied, LU-factorized with the DMMA LU and applied as M^-1 in Q M^-1 u = b,
+ * x = M^-1 u.  The stopping test is still the true residual ||b - Q x|| / ||b||.  nblocks = 0: plain GMRES. */
+int mmr_gmres_bj(mmr_ctx* ctx, int64_t N, const double* d_Q, int64_t ld, const double* d_b, double* d_x,
+                 double tol, int restart, int maxit, int nblocks, const int64_t* block_row0,
+                 const int64_t* block_rows, int* iters_out, double* relres_out);
 
 /* y = Q x for a row block: y[r] = sum_c Q[r*ld + c] x[c], r in [0, nrows). */
 int mmr_matvec(mmr_ctx* ctx, int64_t nrows, int64_t ncols, const double* d_Q, int64_t ld,

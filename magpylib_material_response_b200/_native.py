@@ -103,6 +103,12 @@ _SIGNATURES = {
          ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
          ctypes.POINTER(ctypes.c_double)],
     ),
+    "mmr_gmres_bj": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
+         ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+         ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)],
+    ),
     "mmr_matvec": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p,
@@ -362,6 +368,19 @@ class Context:
         relres = ctypes.c_double(0.0)
         status = self.lib.mmr_gmres(self.handle, b.shape[0], _ptr(Q), ld, _ptr(b), _ptr(x), tol, restart,
                                     maxit, ctypes.byref(iters), ctypes.byref(relres))
+        if status != 0 and (raise_on_fail or status != -4):
+            _check(self.lib, status)
+        return iters.value, relres.value
+
+    def gmres_bj(self, Q, ld, b, x, blocks, tol=1e-10, restart=200, maxit=2000, raise_on_fail=True):
+        """GMRES with a block-Jacobi right preconditioner; blocks = [(first row, rows), ...]."""
+        iters = ctypes.c_int(0)
+        relres = ctypes.c_double(0.0)
+        nb = len(blocks)
+        r0 = (ctypes.c_int64 * max(nb, 1))(*[int(b0) for b0, _ in blocks])
+        rn = (ctypes.c_int64 * max(nb, 1))(*[int(n) for _, n in blocks])
+        status = self.lib.mmr_gmres_bj(self.handle, b.shape[0], _ptr(Q), ld, _ptr(b), _ptr(x), tol, restart, maxit,
+                                       nb, r0, rn, ctypes.byref(iters), ctypes.byref(relres))
         if status != 0 and (raise_on_fail or status != -4):
             _check(self.lib, status)
         return iters.value, relres.value

@@ -128,12 +128,36 @@ __global__ void unpermute_kernel(int64_t N, int64_t tgt_block, int nranks, int64
   y[g] = gathered[rank * maxrows + lrow];
 }
 
+// Block-Jacobi right preconditioner M = blockdiag(D_b): the diagonal blocks of Q of selected row ranges (one
+// magnet each), LU-factorized with the DMMA LU; identity on the other rows.  GMRES then iterates on
+// Q M^-1 u = b, x = M^-1 u; the true residual b - Q x is unaffected.
+struct BjBlock {
+  int64_t r0, nb, ld;
+  double* D;      // nb x ld copy of Q[r0:r0+nb, r0:r0+nb], factorized in place
+  int32_t* ipiv;  // nb
+};
+struct Precond {
+  std::vector<BjBlock> blocks;
+};
+
+// z = M^-1 v (z may alias v)
+int apply_precond(mmr_ctx* ctx, const Precond& pc, int64_t N, const double* v, double* z) {
+  if (z != v) MMR_CUDA(cudaMemcpyAsync(z, v, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (const BjBlock& b : pc.blocks) {
+    const int rc = mmr_lu_solve(ctx, b.nb, b.D, b.ld, b.ipiv, z + b.r0, 1);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 struct Gm {
   mmr_ctx* ctx;
   int64_t N, nrows_local, tgt_block, ld, maxrows;
   const double* Q;
   double* ylocal;
   double* gathered;
+  const Precond* pc = nullptr;
+  double* ptmp = nullptr;  // length N scratch of the preconditioned matvec
 };
 
 int launch_matvec(mmr_ctx* ctx, int64_t nrows, int64_t ncols, const double* Q, int64_t ld, const double* x,
@@ -166,7 +190,7 @@ int apply_Q(const Gm& g, const double* x, double* y) {
 
 int gmres_impl(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block, const double* Q, int64_t ld,
                const double* d_b, double* d_x, double tol, int restart, int maxit, int* iters_out,
-               double* relres_out) {
+               double* relres_out, const Precond* pc = nullptr) {
   if (restart < 1) restart = 1;
   if (restart > maxit) restart = maxit > 0 ? maxit : 1;
   const int m = restart;
@@ -181,15 +205,19 @@ int gmres_impl(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block, 
   size_t off = 0;
   auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 31) & ~(size_t)31; return o; };
   const size_t oV = take(nV), ow = take(N), orr = take(N), oyl = take(g.maxrows), og = take((size_t)R * g.maxrows),
-               oh = take(m + 2), oh2 = take(m + 2), oy = take(m + 1);
+               oh = take(m + 2), oh2 = take(m + 2), oy = take(m + 1), opt = take(pc ? N : 0);
   int rc = mmr_ws2_reserve(ctx, off * sizeof(double));
   if (rc) return rc;
-  rc = mmr_hpin_reserve(ctx, sizeof(double) * (size_t)(2 * m + 16));
+  // (with a preconditioner, mmr_lu_solve keeps pivots + permutation of its block in the same pinned buffer:
+  // reserve the larger need once, so that the buffer never moves under `hh`)
+  rc = mmr_hpin_reserve(ctx, std::max(sizeof(double) * (size_t)(2 * m + 16), 2 * sizeof(int) * (size_t)N + 512));
   if (rc) return rc;
   double* base = (double*)ctx->ws2;
   double *V = base + oV, *w = base + ow, *r = base + orr, *hd = base + oh, *hd2 = base + oh2, *yd = base + oy;
   g.ylocal = base + oyl;
   g.gathered = base + og;
+  g.pc = pc;
+  g.ptmp = base + opt;
   double* hh = (double*)ctx->hpin;  // pinned host mirror of hd (m+2 entries)
   cudaStream_t s = ctx->stream;
   const unsigned gridN = (unsigned)ceil_div64(N, 256);
@@ -211,6 +239,8 @@ int gmres_impl(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block, 
 
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gv(m + 1), yv(m);
   bool converged = false;
+  double prev_relres = -1.0;
+  int stalled = 0;
   while (true) {
     // true residual r = b - Q x  (iterative-refinement check)
     rc = apply_Q(g, d_x, w);
@@ -228,6 +258,14 @@ int gmres_impl(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block, 
       break;
     }
     if (iters >= maxit) break;
+    // stagnation: the true residual no longer follows the implicit one (attainable accuracy reached above tol);
+    // two restart cycles without a 10 % gain end the run instead of grinding to maxit
+    if (prev_relres > 0.0 && relres > 0.9 * prev_relres) {
+      if (++stalled >= 2) break;
+    } else {
+      stalled = 0;
+    }
+    prev_relres = relres;
     scale_copy_kernel<<<gridN, 256, 0, s>>>(N, r, hd, V);  // V_0 = r / beta
     MMR_CHECK_LAUNCH(ctx);
     std::fill(gv.begin(), gv.end(), 0.0);
@@ -235,7 +273,12 @@ int gmres_impl(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block, 
     int j = 0;
     for (; j < m && iters < maxit; ++j) {
       ++iters;
-      rc = apply_Q(g, V + (size_t)j * N, w);
+      if (pc) {
+        if ((rc = apply_precond(ctx, *pc, N, V + (size_t)j * N, g.ptmp))) return rc;
+        rc = apply_Q(g, g.ptmp, w);
+      } else {
+        rc = apply_Q(g, V + (size_t)j * N, w);
+      }
       if (rc) return rc;
       // CGS2
       multi_dot_kernel<<<j + 1, 512, 0, s>>>(N, V, j + 1, w, hd);
@@ -280,12 +323,23 @@ int gmres_impl(mmr_ctx* ctx, int64_t N, int64_t nrows_local, int64_t tgt_block, 
     for (int i = k - 1; i >= 0; --i) {
       double t = gv[i];
       for (int c = i + 1; c < k; ++c) t -= H[(size_t)c * (m + 1) + i] * yv[c];
-      yv[i] = t / H[(size_t)i * (m + 1) + i];
+      const double hii = H[(size_t)i * (m + 1) + i];
+      yv[i] = hii != 0.0 ? t / hii : 0.0;
     }
     for (int i = 0; i < k; ++i) hh[i] = yv[i];
     MMR_CUDA(cudaMemcpyAsync(yd, hh, sizeof(double) * k, cudaMemcpyHostToDevice, s));
-    block_axpy_kernel<<<gridN, 256, 0, s>>>(N, V, k, yd, 1.0, d_x);
-    MMR_CHECK_LAUNCH(ctx);
+    if (pc) {
+      MMR_CUDA(cudaStreamSynchronize(s));  // yd has left the pinned buffer before the block solves reuse it
+      MMR_CUDA(cudaMemsetAsync(g.ptmp, 0, sizeof(double) * N, s));
+      block_axpy_kernel<<<gridN, 256, 0, s>>>(N, V, k, yd, 1.0, g.ptmp);
+      MMR_CHECK_LAUNCH(ctx);
+      if ((rc = apply_precond(ctx, *pc, N, g.ptmp, g.ptmp))) return rc;
+      add_vec_kernel<<<gridN, 256, 0, s>>>((int)N, g.ptmp, d_x);
+      MMR_CHECK_LAUNCH(ctx);
+    } else {
+      block_axpy_kernel<<<gridN, 256, 0, s>>>(N, V, k, yd, 1.0, d_x);
+      MMR_CHECK_LAUNCH(ctx);
+    }
     MMR_CUDA(cudaStreamSynchronize(s));  // hh is reused next round
   }
   if (iters_out) *iters_out = iters;
@@ -324,6 +378,71 @@ extern "C" int mmr_gmres(mmr_ctx* ctx, int64_t N, const double* d_Q, int64_t ld,
   ctx->nranks = 1;  // single-GPU entry point: never touches the communicator
   const int rc = gmres_impl(ctx, N, N, (N + 2) / 3, d_Q, ld, d_b, d_x, tol, restart, maxit, iters_out, relres_out);
   ctx->nranks = saved;
+  return rc;
+}
+
+extern "C" int mmr_gmres_bj(mmr_ctx* ctx, int64_t N, const double* d_Q, int64_t ld, const double* d_b, double* d_x,
+                            double tol, int restart, int maxit, int nblocks, const int64_t* block_row0,
+                            const int64_t* block_rows, int* iters_out, double* relres_out) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  MMR_ARG(N >= 0 && ld >= N, "bad N/ld");
+  if (iters_out) *iters_out = 0;
+  if (relres_out) *relres_out = 0.0;
+  if (N == 0) return 0;
+  MMR_ARG(d_Q && d_b && d_x, "NULL pointer");
+  MMR_ARG(tol > 0 && maxit >= 0, "bad tol/maxit");
+  MMR_ARG(nblocks >= 0 && (nblocks == 0 || (block_row0 && block_rows)), "bad block list");
+  DeviceGuard g(ctx->device);
+  Precond pc;
+  int rc = 0;
+  auto release = [&]() {
+    for (BjBlock& b : pc.blocks) {
+      if (b.D) cudaFree(b.D);
+      if (b.ipiv) cudaFree(b.ipiv);
+    }
+  };
+  for (int i = 0; i < nblocks && rc == 0; ++i) {
+    BjBlock b;
+    b.r0 = block_row0[i];
+    b.nb = block_rows[i];
+    if (b.nb <= 0) continue;
+    if (b.r0 < 0 || b.r0 + b.nb > N) {
+      mmr_set_error("invalid argument: preconditioner block %d outside the matrix", i);
+      rc = -1;
+      break;
+    }
+    b.ld = (b.nb + 15) / 16 * 16;
+    b.D = nullptr;
+    b.ipiv = nullptr;
+    cudaError_t e = cudaMalloc((void**)&b.D, sizeof(double) * (size_t)b.nb * b.ld);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b.ipiv, sizeof(int32_t) * (size_t)b.nb);
+    pc.blocks.push_back(b);
+    if (e != cudaSuccess) {
+      rc = mmr_fail_cuda(e, "allocate preconditioner block", __FILE__, __LINE__);
+      break;
+    }
+    e = cudaMemcpy2DAsync(b.D, sizeof(double) * b.ld, d_Q + b.r0 * ld + b.r0, sizeof(double) * ld, sizeof(double) * b.nb,
+                          (size_t)b.nb, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      rc = mmr_fail_cuda(e, "copy preconditioner block", __FILE__, __LINE__);
+      break;
+    }
+    int info = 0;
+    rc = mmr_lu_factor(ctx, b.nb, b.D, b.ld, b.ipiv, &info);
+    if (rc == 0 && info != 0) {
+      mmr_set_error("block-Jacobi preconditioner: diagonal block %d is singular (pivot %d)", i, info);
+      rc = -8;
+    }
+  }
+  if (rc == 0) {
+    const int saved = ctx->nranks;
+    ctx->nranks = 1;
+    rc = gmres_impl(ctx, N, N, (N + 2) / 3, d_Q, ld, d_b, d_x, tol, restart, maxit, iters_out, relres_out,
+                    pc.blocks.empty() ? nullptr : &pc);
+    ctx->nranks = saved;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  release();
   return rc;
 }
 

@@ -509,8 +509,34 @@ def _solve_cells_sharded(ctx, pos, quat, dim, chi, rhs, *, pairs_matching, max_d
     return x, info
 
 
+BJ_MIN_CHI = 10.0   # a magnet whose largest susceptibility reaches this gets its own preconditioner block
+BJ_MIN_CELLS = 64
+
+
+def _precond_blocks(groups, chi):
+    """Row ranges [(first row, rows)] of the block-Jacobi preconditioner of ``solver="gmres"``: the magnets
+    (``groups`` = cell counts in order) that are strongly susceptible -- those make Q = I - chi N ill
+    conditioned (cond ~ 1 + chi) -- provided factorizing their diagonal blocks is clearly cheaper than
+    factorizing Q itself.  None: plain GMRES."""
+    if not groups or len(groups) < 2:
+        return None
+    n = int(sum(groups))
+    if n != len(chi):
+        return None
+    blocks, c0 = [], 0
+    for m in groups:
+        m = int(m)
+        if m >= BJ_MIN_CELLS and float(np.abs(chi[c0:c0 + m]).max()) >= BJ_MIN_CHI:
+            blocks.append((3 * c0, 3 * m))
+        c0 += m
+    if not blocks or sum(float(nb) ** 3 for _, nb in blocks) > 0.3 * float(3 * n) ** 3:
+        return None
+    return blocks
+
+
 def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching=False, max_dist=0,
-                       split=1, solver="lu", tol=1e-12, device=None, min_log_time=None, demag_store=None):
+                       split=1, solver="lu", tol=1e-12, device=None, min_log_time=None, demag_store=None,
+                       groups=None):
     """Host arrays in, host array out: assemble Q = I - chi*N on the device, solve
     Q x = J0 + chi*H_ext (demag.py:444-470).  All (n,3) arrays, GLOBAL frame.  Returns (x, info).
 
@@ -567,7 +593,13 @@ def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching
             d_b = d_x
             d_x = d_b.clone()
             ev[2].record(ctx.stream)
-            iters, relres = ctx.gmres(Q, ld, d_b, d_x, tol=tol, restart=min(300, N), maxit=max(1000, 2 * N))
+            blocks = _precond_blocks(groups, np.asarray(chi, dtype=float).reshape(n, 3))
+            if blocks:
+                # several magnets, some of them strongly susceptible: block-Jacobi over those magnets
+                iters, relres = ctx.gmres_bj(Q, ld, d_b, d_x, blocks, tol=tol, restart=min(300, N), maxit=max(1000, 2 * N))
+                info["gmres_precond_blocks"] = blocks
+            else:
+                iters, relres = ctx.gmres(Q, ld, d_b, d_x, tol=tol, restart=min(300, N), maxit=max(1000, 2 * N))
             info["gmres_iters"], info["gmres_relres"] = iters, relres
         ev[3].record(ctx.stream)
         x = d_x.cpu().numpy().reshape(n, 3)
@@ -578,7 +610,7 @@ def solve_cells_global(pos, quat, dim, pol_global, chi, H_ext, *, pairs_matching
 
 
 def apply_demag_arrays(pos, quat, dim, pol, chi, H_ext=None, *, pairs_matching=False, max_dist=0, split=1,
-                       solver="lu", tol=1e-12, device=None, return_info=False, demag_store=None):
+                       solver="lu", tol=1e-12, device=None, return_info=False, demag_store=None, groups=None):
     """Array-level form of ``apply_demag`` (structure-of-arrays in host memory, no objects):
     pos (n,3), quat (n,4) scalar-last, dim (n,3), pol (n,3) LOCAL-frame polarizations, chi scalar /
     (3,) / (n,) / (n,3), H_ext (n,3) or (3,).  Returns the solved LOCAL-frame polarizations (n,3).
@@ -603,7 +635,7 @@ def apply_demag_arrays(pos, quat, dim, pol, chi, H_ext=None, *, pairs_matching=F
     rot = R.from_quat(quat)
     x, info = solve_cells_global(pos, quat, dim, rot.apply(pol), chi_a, H, pairs_matching=pairs_matching,
                                  max_dist=max_dist, split=split, solver=solver, tol=tol, device=device,
-                                 demag_store=demag_store)
+                                 demag_store=demag_store, groups=groups)
     out = rot.apply(x, inverse=True)
     return (out, info) if return_info else out
 
@@ -710,7 +742,7 @@ def apply_demag(
         pol_new, solve_info = solve_cells_global(
             pos, quat, dim, pol_global, chi, H_ext, pairs_matching=pairs_matching, max_dist=max_dist,
             split=split, solver=solver, tol=tol, device=device, min_log_time=min_log_time,
-            demag_store=demag_store,
+            demag_store=demag_store, groups=cells.sizes,
         )
         info.update(solve_info)
 

@@ -276,3 +276,16 @@ def test_c_abi_library_exports_every_declared_symbol():
         status = lib.mmr_ctx_create(0, None, ctypes.byref(handle))
         assert status != 0
         assert b"no CPU fallback" in lib.mmr_last_error()
+
+
+def test_gmres_block_jacobi_block_selection():
+    from magpylib_material_response_b200.demag import _precond_blocks
+
+    chi = np.vstack([np.full((4000, 3), 0.5), np.full((4000, 3), 1000.0)])
+    assert _precond_blocks([4000, 4000], chi) == [(12000, 12000)]  # only the soft magnet
+    assert _precond_blocks([8000], np.full((8000, 3), 1000.0)) is None  # one magnet: the block would be Q itself
+    assert _precond_blocks([4000, 4000], np.full((8000, 3), 0.5)) is None  # nothing ill conditioned
+    assert _precond_blocks(None, chi) is None
+    many = np.full((2700, 3), 50.0)
+    assert _precond_blocks([100] * 27, many) == [(300 * k, 300) for k in range(27)]
+    assert _precond_blocks([10] * 270, many) is None  # tiny magnets are left alone
