@@ -286,7 +286,7 @@ class Context:
         t0 = (ctypes.c_double * cap)()
         dt = (ctypes.c_double * cap)()
         n = self.lib.mmr_ctx_profile_timeline(self.handle, kinds, t0, dt, cap)
-        tag = ("", "@side", "@comm")
+        tag = ("", "@side", "@comm", "@aux")
         return [(self.PROF_KINDS[kinds[i] & 0xFF] + tag[(kinds[i] >> 8) & 3], t0[i], dt[i]) for i in range(n)]
 
     def profile_records(self, kind, cap=100000):

@@ -69,7 +69,7 @@ int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s) {
   if (!ctx->profiling) return -1;
   mmr_ctx::ProfRec r;
   r.kind = kind;
-  r.side = (s == ctx->side) ? 1 : ((ctx->comm && s == ctx->comm) ? 2 : 0);
+  r.side = (s == ctx->side) ? 1 : ((ctx->comm && s == ctx->comm) ? 2 : ((ctx->aux && s == ctx->aux) ? 3 : 0));
   r.e0 = prof_event(ctx);
   r.e1 = prof_event(ctx);
   r.units = 0.0;
@@ -108,6 +108,7 @@ extern "C" int64_t mmr_ctx_profile_timeline(mmr_ctx* ctx, int* kind_out, double*
   cudaStreamSynchronize(ctx->stream);
   if (ctx->side) cudaStreamSynchronize(ctx->side);
   if (ctx->comm) cudaStreamSynchronize(ctx->comm);
+  if (ctx->aux) cudaStreamSynchronize(ctx->aux);
   int64_t cnt = 0;
   for (auto& r : ctx->prof) {
     if (cnt >= cap) break;
@@ -190,6 +191,7 @@ extern "C" int mmr_ctx_create(int device, void* stream, mmr_ctx** out) {
     MMR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     MMR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));  // panel look-ahead stream
     MMR_CUDA(cudaStreamCreateWithPriority(&c->comm, cudaStreamNonBlocking, hi));  // broadcasts of the distributed LU
+    MMR_CUDA(cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, lo));   // deferred, off the critical path
     const char* la = getenv("MMR_LU_LOOKAHEAD");
     c->lookahead = !(la && la[0] == '0');
   }
@@ -220,6 +222,7 @@ extern "C" int mmr_ctx_destroy(mmr_ctx* ctx) {
     if (ctx->evd[i]) cudaEventDestroy(ctx->evd[i]);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->comm) cudaStreamDestroy(ctx->comm);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   delete ctx;
   return 0;
 }

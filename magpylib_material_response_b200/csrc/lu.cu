@@ -1251,20 +1251,6 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// *fail = kb + 1 (if still 0) when any |S[r, c]| > 1 (or NaN) for r in [r0, m), c in [0, nb)
-__global__ void __launch_bounds__(256)
-    lu_spec_check_kernel(const double* __restrict__ S, int64_t lds, int r0, int m, int nb, int* __restrict__ fail, int kb) {
-  if (mmr_gemm::lu_poisoned(mmr_gemm::lu_failword(fail), kb)) return;
-  const int64_t rows = m - r0;
-  const int64_t total = rows * nb;
-  bool bad = false;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = e % rows, c = e / rows;
-    bad |= !(fabs(S[c * lds + r0 + r]) <= 1.0);
-  }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicCAS(fail, 0, kb + 1);
-}
-
 // unless this or an earlier panel was rejected: A[kb + r, kb + c] = S[r, c] for r < m, c < nb; ipiv[kb + c] = kb + c
 __global__ void __launch_bounds__(256)
     lu_spec_commit_kernel(const double* __restrict__ S, int64_t lds, int m, int nb, double* __restrict__ A,
@@ -1661,15 +1647,8 @@ template <bool FWD>
 __global__ void __launch_bounds__(SWEEP_THREADS)
     lu_sweep_kernel(const double* __restrict__ Al, int64_t ld, int N, int obw, int R, int me, int s_done, int s_next,
                     int far_lo, int far_hi, double* __restrict__ b, void* const* __restrict__ peers, int epoch,
-                    int* __restrict__ p2p_err, long long* __restrict__ clk) {
+                    int* __restrict__ p2p_err) {
   __shared__ double xs[2 * NB], ys[2 * NB], zs[2 * NB];
-  int nclk = 0;
-#define SWEEP_STAMP()                                                       \
-  do {                                                                      \
-    if (clk && threadIdx.x == 0 && nclk < 16) clk[blockIdx.x == 0 ? nclk : 16 + nclk] = clock64(); \
-    ++nclk;                                                                 \
-  } while (0)
-  SWEEP_STAMP();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u0 = s_done >= 0 ? s_done * obw : 0;
   const int nu = s_done >= 0 ? min(obw, N - u0) : 0;
@@ -1728,17 +1707,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
         if (g < N) b[g] -= a;
       }
     }
-    if (blockIdx.x == 1) SWEEP_STAMP();
     return;
   }
   if (s_next < 0) return;
   const int d0 = s_next * obw;
   const int nd = min(obw, N - d0), na = min(NB, nd);
   const double* blk = Al + (int64_t)((s_next / R) * obw) * ld;  // local column of global column d0
-  SWEEP_STAMP();  // 1: prefetches issued, flag seen
   for (int i = tid; i < nu; i += blockDim.x) xs[i] = xsrc[u0 + i];
   __syncthreads();
-  SWEEP_STAMP();  // 2: x staged
   // Warp w owns the columns j = w + SWEEP_WARPS c, c < SWEEP_NC, of the block.  A product phase is latency bound (a handful of
   // DRAM round trips), so every lane first issues the loads of ALL eight columns and only then reduces: one
   // memory latency per phase instead of one per column.
@@ -1788,7 +1764,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
     if (lane == 0 && j < nd) ys[j] = b[d0 + j] - sm[c];
   }
   __syncthreads();
-  SWEEP_STAMP();  // 3: update by s_done
   // (2) the block itself: two panels a = [0, na), q = [na, nd) with inverted diagonal blocks
   if (FWD) {
     // w_a = U_aa^-T y_a   and, for the columns of q, the part of U_qq^-T y_q ... no: y_q is not final yet
@@ -1835,7 +1810,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
     }
   }
   __syncthreads();
-  SWEEP_STAMP();  // 4: both panels
   for (int j = tid; j < nd; j += blockDim.x) b[d0 + j] = zs[j];
   if (peers) {
     // publish the finished block: data into every rank's buffer (mine included), then the flags
@@ -1850,8 +1824,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
       *flag = epoch;
     }
   }
-  SWEEP_STAMP();  // 5: published
-#undef SWEEP_STAMP
 }
 
 // every block flag of a sweep has reached this rank (value == epoch); gives up after ~2 s
@@ -1891,7 +1863,6 @@ static int lu_sweeps_inv(mmr_ctx* ctx, cudaStream_t st, int N, int obw, int R, i
     epoch = ++ctx->p2p_epoch;
   }
   auto step = [&](bool fwd, int s_done, int s_next_global) -> int {
-    long long* clk = nullptr;
     // my columns that receive the update by s_done, and whether I finish s_next
     const bool own_next = s_next_global >= 0 && s_next_global % R == me;
     int far_lo = 0, far_hi = 0;
@@ -1912,10 +1883,10 @@ static int lu_sweeps_inv(mmr_ctx* ctx, cudaStream_t st, int N, int obw, int R, i
     const unsigned grid = 1 + (unsigned)std::min<int64_t>(ctx->sm_count - 1, ceil_div64(nfar, 4 * SWEEP_WARPS));
     if (fwd)
       lu_sweep_kernel<true><<<grid, SWEEP_THREADS, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
-                                                  far_hi, d_b, peers, epoch, p2p_err, clk);
+                                                  far_hi, d_b, peers, epoch, p2p_err);
     else
       lu_sweep_kernel<false><<<grid, SWEEP_THREADS, 0, st>>>(Al, ld, N, obw, R, me, s_done, own_next ? s_next_global : -1, far_lo,
-                                                   far_hi, d_b, peers, epoch, p2p_err, clk);
+                                                   far_hi, d_b, peers, epoch, p2p_err);
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   };
@@ -1994,8 +1965,18 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   // inverse stash: L11^-1 | U11^-1 of every panel, written into the diagonal blocks at the end if no panel was
   // rejected (inverse format, see lu_sweep_kernel)
   const int npanel_slots = 2 * (int)ceil_div64(N, OB);
-  const size_t stash_bytes = spec_on ? sizeof(double) * (size_t)npanel_slots * 2 * NB * NB : 0;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 4 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes + stash_bytes);
+  const size_t stash_bytes = spec_on ? ((sizeof(double) * (size_t)npanel_slots * 2 * NB * NB + 255) / 256 * 256) : 0;
+  // deferred-TRSM path (see run()): two W = L21 L_blk^-1 buffers (N x OB) and one N x NB temporary
+  static int defer_default = -1;
+  if (defer_default < 0) {
+    const char* e = getenv("MMR_LU_DEFER_TRSM");  // 0: U12 = L_blk^-1 A12 before every trailing update (round 1)
+    defer_default = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool defer_trsm = spec_on && ctx->lookahead && defer_default && OB == 2 * NB && N > 4 * OB;
+  const size_t wbuf_bytes = defer_trsm ? ((sizeof(double) * (size_t)N * OB + 255) / 256 * 256) : 0;
+  const size_t tbuf_bytes = defer_trsm ? ((sizeof(double) * (size_t)N * NB + 255) / 256 * 256) : 0;
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 4 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes + stash_bytes +
+                                   2 * wbuf_bytes + tbuf_bytes);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 256);
   if (rc) return rc;
@@ -2006,6 +1987,8 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   void* d_spec = (char*)Lbuf + 4 * sizeof(double) * NB * NB;
   double* Sbuf = (double*)((char*)d_spec + spec_bytes);
   double* stash = (double*)((char*)Sbuf + sbuf_bytes);
+  double* Wbuf[2] = {(double*)((char*)stash + stash_bytes), (double*)((char*)stash + stash_bytes + wbuf_bytes)};
+  double* Tbuf = (double*)((char*)stash + stash_bytes + 2 * wbuf_bytes);
   auto slot_of = [&](int kb) { return stash + (size_t)(2 * (kb / OB) + ((kb % OB) ? 1 : 0)) * 2 * NB * NB; };
   // inverse of the unit-lower diagonal block of inner panel `inner` of the outer block at kb
   auto Linv = [&](int kb, int inner) { return Lbuf + (size_t)((((kb / OB) & 1) << 1) + inner) * NB * NB; };
@@ -2101,6 +2084,47 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   const bool lookahead = ctx->lookahead;
   // One pass over the outer blocks from kb0 on.  Entry state: everything left of kb0 is factored and applied,
   // block kb0 has received all earlier updates (and, with first_inner = 1, its panel 0 is done).
+  // Deferred TRSM (speculative mode, full two-panel blocks).  The trailing update needs U12 = L_blk^-1 A12, three
+  // small dependent launches (L00^-1, the L10 coupling, L11^-1) that sat on the main stream in front of every
+  // big GEMM: 17 ms of a 309 ms factorization at N = 24000, at 6.5 TFLOP/s.  By associativity
+  //     A22 -= L21 (L_blk^-1 A12) = (L21 L_blk^-1) A12 = W A12,      W L_blk = L21,
+  // so the big GEMM can run on the UNTOUCHED rows A12 with W in place of L21; W (three m x 128 x 128 products)
+  // is built on the communication stream while the main stream does the narrow look-ahead update, and the
+  // U12 rows themselves -- needed by nobody before the final solve -- are finalised afterwards on a
+  // low-priority stream, concurrently with the next block's GEMM.
+  cudaStream_t cm_s = ctx->comm, aux_s = ctx->aux;
+  cudaEvent_t e_it = ctx->evd[0], e_W[2] = {ctx->evd[1], ctx->evd[2]}, e_bulk[2] = {ctx->evd[3], ctx->evd[4]},
+              e_trsm[2] = {ctx->evd[5], ctx->evd[6]}, e_join = ctx->evd[7];
+  bool par_used[2] = {false, false};
+  auto build_W = [&](int kb, int par) -> int {  // on cm_s; block [kb, kb + 2 NB) is factored and committed
+    const int m = N - kb - OB, mW = m, dep = kb + NB;
+    double* W = Wbuf[par];
+    const double* L21a = A + (int64_t)kb * ld + kb + OB;
+    const double* L21b = A + (int64_t)(kb + NB) * ld + kb + OB;
+    const double* L10 = A + (int64_t)kb * ld + kb + NB;
+    int ps = mmr_prof_begin(ctx, MMR_PROF_PANEL_GEMM, cm_s);
+    int r = mmr_dgemm_launch(ctx, cm_s, m, NB, NB, 1.0, L21b, ld, Linv(kb, 1), NB, 0.0, W + (size_t)NB * mW, mW, d_fail, dep);
+    if (r) return r;
+    {
+      const unsigned g = (unsigned)std::min<int64_t>((int64_t)4 * ctx->sm_count, ceil_div64((int64_t)m * NB, 256 * 8));
+      lu_copy_guarded_kernel<<<g, 256, 0, cm_s>>>(L21a, ld, m, NB, Tbuf, mW, d_fail, dep);
+      MMR_CHECK_LAUNCH(ctx);
+    }
+    if ((r = mmr_dgemm_launch(ctx, cm_s, m, NB, NB, -1.0, W + (size_t)NB * mW, mW, L10, ld, 1.0, Tbuf, mW, d_fail, dep))) return r;
+    if ((r = mmr_dgemm_launch(ctx, cm_s, m, NB, NB, 1.0, Tbuf, mW, Linv(kb, 0), NB, 0.0, W, mW, d_fail, dep))) return r;
+    mmr_prof_end(ctx, ps, 6.0 * m * (double)NB * NB, cm_s);
+    return 0;
+  };
+  // U12 rows of the columns [cb, ce): the first three steps of update_cols, on stream s
+  auto finish_U12 = [&](cudaStream_t s, int kb, int cb, int ce) -> int {
+    const int dep = kb + NB;
+    int r = trsm(s, Linv(kb, 0), kb, NB, cb, ce, dep);
+    if (r) return r;
+    if ((r = gemm(s, MMR_PROF_TRSM, kb + NB, kb + OB, kb, NB, cb, ce, dep))) return r;
+    return trsm(s, Linv(kb, 1), kb + NB, NB, cb, ce, dep);
+  };
+  // One pass over the outer blocks from kb0 on.  Entry state: everything left of kb0 is factored and applied,
+  // block kb0 has received all earlier updates (and, with first_inner = 1, its panel 0 is done).
   auto run = [&](int kb0, int first_inner) -> int {
     int r = factor_outer(main_s, kb0, min(OB, N - kb0), first_inner);
     if (r) return r;
@@ -2111,19 +2135,52 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
       if ((r = laswp(main_s, 0, kb, pslot(kb, 0), ob > NB ? pslot(kb, 1) : -1, last_panel(kb)))) return r;
       if (next >= N) break;
       const int ob2 = min(OB, N - next);
-      if ((r = update_cols(kb, ob, next, next + ob2))) return r;
+      const int cb2 = next + ob2;  // first bulk column
+      const int par = (kb / OB) & 1;
+      const bool use_W = defer_trsm && spec_on && ob == OB && N - cb2 >= 4 * NB;
+      if (use_W) {
+        // W of this block on the communication stream, beside the narrow update below
+        MMR_CUDA(cudaEventRecord(e_it, main_s));
+        MMR_CUDA(cudaStreamWaitEvent(cm_s, e_it, 0));
+        if (par_used[par]) MMR_CUDA(cudaStreamWaitEvent(cm_s, e_bulk[par], 0));  // the GEMM that read this W buffer
+        if ((r = build_W(kb, par))) return r;
+        MMR_CUDA(cudaEventRecord(e_W[par], cm_s));
+      }
+      if ((r = update_cols(kb, ob, next, cb2))) return r;
       if (lookahead) {
         MMR_CUDA(cudaEventRecord(ctx->ev[0], main_s));
-        if ((r = update_cols(kb, ob, next + ob2, N))) return r;
+        if (use_W) {
+          MMR_CUDA(cudaStreamWaitEvent(main_s, e_W[par], 0));
+          const int m = N - next;
+          const int ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, main_s);
+          r = mmr_dgemm_launch(ctx, main_s, m, N - cb2, OB, -1.0, Wbuf[par], m, A + (int64_t)cb2 * ld + kb, ld, 1.0,
+                               A + (int64_t)cb2 * ld + next, ld, d_fail, kb + NB);
+          if (r) return r;
+          mmr_prof_end(ctx, ps, 2.0 * m * (double)(N - cb2) * OB, main_s);
+          MMR_CUDA(cudaEventRecord(e_bulk[par], main_s));
+          MMR_CUDA(cudaStreamWaitEvent(aux_s, e_bulk[par], 0));
+          if ((r = finish_U12(aux_s, kb, cb2, N))) return r;
+          MMR_CUDA(cudaEventRecord(e_trsm[par], aux_s));
+          par_used[par] = true;
+        } else {
+          if ((r = update_cols(kb, ob, cb2, N))) return r;
+        }
         MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
+        // the L11^-1 buffers of block `next` are those of block kb - OB: its deferred U12 rows must be done
+        if (par_used[par ^ 1]) MMR_CUDA(cudaStreamWaitEvent(side_s, e_trsm[par ^ 1], 0));
         if ((r = factor_outer(side_s, next, ob2, 0))) return r;
         MMR_CUDA(cudaEventRecord(ctx->ev[1], side_s));
         MMR_CUDA(cudaStreamWaitEvent(main_s, ctx->ev[1], 0));
       } else {
-        if ((r = update_cols(kb, ob, next + ob2, N))) return r;
+        if ((r = update_cols(kb, ob, cb2, N))) return r;
         if ((r = factor_outer(main_s, next, ob2, 0))) return r;
       }
     }
+    // whatever follows on the main stream comes after the deferred work
+    MMR_CUDA(cudaEventRecord(e_join, cm_s));
+    MMR_CUDA(cudaStreamWaitEvent(main_s, e_join, 0));
+    MMR_CUDA(cudaEventRecord(e_join, aux_s));
+    MMR_CUDA(cudaStreamWaitEvent(main_s, e_join, 0));
     return 0;
   };
   int* h_info = (int*)ctx->hpin;
