@@ -594,13 +594,22 @@ def run_ours(args):
         d_x.zero_()
         return ctx.gmres_dist(N, 3 * n_local, tgt_block, Q, ld, d_rhs, d_x, tol=args.tol, restart=args.restart, maxit=5000)
 
-    for _ in range(args.warmup):
+    # The timed region records event pairs only for the kernel classes the line reports a roofline for (the LU
+    # trailing GEMM, the assembly, the matvec, the triangular sweeps): every recorded launch costs two event
+    # records of host time, which shows in the multi-GPU step where the panel chain exposes the host (5 ms of a
+    # 68 ms step at 8 GPUs with everything recorded).  The full per-stage table comes from one extra, untimed
+    # step after the timed region.  The last warm-up step runs with the same records so that the event pool
+    # exists before the clock starts.
+    timed_kinds = ["assemble", "gemm", "matvec", "trisolve"]
+    for it in range(args.warmup):
+        if it == args.warmup - 1:
+            ctx.set_profiling(True, kinds=timed_kinds)
         step()
     barrier()
     peaks = load_peaks(ctx)  # FP64 peaks measured now, clocks already up from the warm-up steps
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ctx.set_profiling(True)
+    ctx.set_profiling(True, kinds=timed_kinds)
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -611,8 +620,13 @@ def run_ours(args):
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
     prof = ctx.profile()
-    ctx.set_profiling(False)
     launches = ctx.launch_count - launches0
+    # one more step, untimed, with every class recorded: the per-stage table
+    ctx.set_profiling(True)
+    step()
+    barrier()
+    prof_all = ctx.profile()
+    ctx.set_profiling(False)
     clocks = sampler.stop() if sampler else None
     if world > 1:
         tt = torch.tensor([t_dev], dtype=torch.float64, device=ctx.device)
@@ -724,7 +738,8 @@ def run_ours(args):
     else:
         roofline = roof_asm
 
-    stages = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps} for k, v in prof.items() if v[2]}
+    stages = {k: {"ms": v[0], "launches": v[2]} for k, v in prof_all.items() if v[2]}
+    stages["_note"] = "one untimed step after the timed region with every kernel class recorded (event pairs per launch)"
     lu_flops = (2.0 / 3.0) * N**3
     # stages overlap (look-ahead) / are per rank: use the step time minus assembly and the solve
     lu_ms = t_step * 1e3 - (prof["assemble"][0] + prof["trisolve"][0]) / args.steps

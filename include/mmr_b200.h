@@ -81,6 +81,8 @@ int64_t mmr_ctx_launch_count(mmr_ctx* ctx);
 #define MMR_PROF_TRISOLVE 7   /* units: matrix bytes streamed                   */
 #define MMR_PROF_COMM 8       /* units: bytes broadcast / gathered (NCCL calls)   */
 #define MMR_PROF_NKINDS 9
+/* on = 0: off; 1: every class; otherwise a mask with bit (k + 1) set for every class k to record (event pairs
+ * cost host time per launch: a timed region records only the classes it reports). */
 int mmr_ctx_set_profiling(mmr_ctx* ctx, int on);
 int mmr_ctx_profile(mmr_ctx* ctx, int kind, double* ms_out, double* units_out,
                     int64_t* launches_out);

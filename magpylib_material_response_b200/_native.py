@@ -267,8 +267,15 @@ class Context:
 
     PROF_KINDS = ("assemble", "gemm", "panel", "trsm", "laswp", "matvec", "panel_gemm", "trisolve", "comm")
 
-    def set_profiling(self, on=True):
-        _check(self.lib, self.lib.mmr_ctx_set_profiling(self.handle, int(bool(on))))
+    def set_profiling(self, on=True, kinds=None):
+        """Record CUDA-event pairs around the native launches (clears earlier records).  kinds: only these
+        kernel classes (names of PROF_KINDS) -- every recorded launch costs two event records of host time."""
+        flag = int(bool(on))
+        if on and kinds is not None:
+            flag = 0
+            for name in kinds:
+                flag |= 1 << (self.PROF_KINDS.index(name) + 1)
+        _check(self.lib, self.lib.mmr_ctx_set_profiling(self.handle, flag))
 
     def profile(self):
         """{kind: (ms, units, launches)} for every kernel class recorded since set_profiling."""

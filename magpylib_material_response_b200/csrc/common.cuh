@@ -43,6 +43,7 @@ struct mmr_ctx {
   int p2p_epoch = 0;
   // optional profiling records (mmr_ctx_set_profiling)
   bool profiling = false;
+  unsigned prof_mask = ~0u;  // bit k: record kernel class k (mmr_ctx_set_profiling)
   struct ProfRec {
     int kind;
     int side;  // 0: main stream, 1: side (look-ahead) stream, 2: communication stream

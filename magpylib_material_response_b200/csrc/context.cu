@@ -66,7 +66,7 @@ static cudaEvent_t prof_event(mmr_ctx* ctx) {
 }
 
 int mmr_prof_begin(mmr_ctx* ctx, int kind, cudaStream_t s) {
-  if (!ctx->profiling) return -1;
+  if (!ctx->profiling || !((ctx->prof_mask >> kind) & 1u)) return -1;
   mmr_ctx::ProfRec r;
   r.kind = kind;
   r.side = (s == ctx->side) ? 1 : ((ctx->comm && s == ctx->comm) ? 2 : ((ctx->aux && s == ctx->aux) ? 3 : 0));
@@ -94,6 +94,7 @@ extern "C" int mmr_ctx_set_profiling(mmr_ctx* ctx, int on) {
   }
   ctx->prof.clear();
   ctx->profiling = on != 0;
+  ctx->prof_mask = (on == 0 || on == 1) ? ~0u : ((unsigned)on >> 1);  // on = 1: every class; else bit k+1 <-> class k
   if (on) {
     if (!ctx->prof_base) MMR_CUDA(cudaEventCreate(&ctx->prof_base));
     MMR_CUDA(cudaEventRecord(ctx->prof_base, ctx->stream));
