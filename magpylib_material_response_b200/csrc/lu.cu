@@ -19,6 +19,7 @@
 
 #include "comm.h"
 #include "dgemm.cuh"
+#include "dgemm_tma.cuh"
 #include "panel128.cuh"
 
 namespace cg = cooperative_groups;
@@ -845,6 +846,35 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     grid.z = 2;
   }
   const GemmAlt alt_v = alt ? *alt : GemmAlt();
+  // C -= A B with all three operands 16-byte aligned, even leading dimensions and even m: the kernels of
+  // dgemm_tma.cuh move C by bulk copies (TMA) through shared memory instead of strided LDG / STG.
+  //   MMR_DGEMM_TMA     = minimum number of tiles for the per-tile TMA kernel (default: one full wave; 0 = never)
+  //   MMR_DGEMM_PERSIST = minimum tiles per group for the persistent kernel (default 0 = never: a grid that holds
+  //                       every SM for the whole update keeps the look-ahead panel chain of the LU waiting)
+  static int tma_min_tiles = -1, persist_min_rounds = -1;
+  if (tma_min_tiles < 0) {
+    const char* e = getenv("MMR_DGEMM_TMA");
+    tma_min_tiles = e ? atoi(e) : 2 * ctx->sm_count;
+    e = getenv("MMR_DGEMM_PERSIST");
+    persist_min_rounds = e ? atoi(e) : 0;
+  }
+  const bool tma_ok = fast_ok && subtract && !alt && check_val == 0 && ntiles < (1LL << 30) && (uintptr_t)C % 16 == 0 &&
+                      ldc % 2 == 0 && m % 2 == 0;
+  if (tma_ok && persist_min_rounds > 0 && ntiles >= (int64_t)persist_min_rounds * 2 * ctx->sm_count) {
+    auto kern = dgemm_sub_persist_kernel<true, 0>;
+    if ((arc = mmr_func_smem(ctx, (const void*)kern, P_SMEM_BYTES))) return arc;
+    kern<<<ctx->sm_count, P_THREADS, P_SMEM_BYTES, s>>>((int)m, (int)n, (int)k, A, lda, B, ldb, C, ldc, (int)grid.x, (int)ntiles,
+                                                        fail, dep);
+    MMR_CHECK_LAUNCH(ctx);
+    return 0;
+  }
+  if (tma_ok && tma_min_tiles > 0 && ntiles >= tma_min_tiles) {
+    auto kern = dgemm_sub_tma_kernel<0>;
+    if ((arc = mmr_func_smem(ctx, (const void*)kern, T_SMEM_BYTES))) return arc;
+    kern<<<grid, THREADS, T_SMEM_BYTES, s>>>((int)m, (int)n, (int)k, A, lda, B, ldb, C, ldc, fail, dep);
+    MMR_CHECK_LAUNCH(ctx);
+    return 0;
+  }
   if (fast_ok) {
     // L2 prefetch distance for the C tiles: the number of CTAs resident at once (2 per SM)
     const int pf = (prefetch_on && !alt && ntiles > 2 * (int64_t)ctx->sm_count) ? 2 * ctx->sm_count : 0;
