@@ -24,6 +24,8 @@
 // accumulator-layout accesses are bank-conflict free) + 2 mbarriers = 229 392 B of the 232 448 B a CTA may use.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include "dgemm.cuh"
 
 namespace mmr_gemm {
@@ -69,6 +71,15 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// BAR.SYNC.DEFER_BLOCKING lets a warp run on past the barrier until its next instruction that touches barrier-
+// protected state; a bulk-copy issue (UBLKCP / UTMALDG) is not such an instruction.  A bulk copy that must come
+// after a CTA barrier therefore takes part of its operands from a shared-memory load behind that barrier: this
+// returns 0 through a load the hardware has to hold back until the barrier has completed.
+__device__ __forceinline__ unsigned after_barrier_zero(const void* smem_word) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];\n\tand.b32 %0, %0, 0;\n" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(smem_word)) : "memory");
+  return v;
+}
 // global -> shared bulk copy (SASS UBLKCP), bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
@@ -254,9 +265,10 @@ __global__ void __launch_bounds__(P_THREADS, 1)
         const int rows = min(BM, m - tm * BM), cols = min(BN, n - tn * BN);
         const int c0 = warp * (BN / 8);
         double* dst = C + (int64_t)(tn * BN + c0) * ldc + tm * BM;
+        const unsigned zs = after_barrier_zero(Cs);
 #pragma unroll
         for (int c = 0; c < BN / 8; ++c)
-          if (c0 + c < cols) bulk_s2g(dst + (int64_t)c * ldc, Cs + (c0 + c) * LDC_S, (unsigned)rows * 8u);
+          if (c0 + c < cols) bulk_s2g(dst + (int64_t)c * ldc, Cs + (c0 + c) * LDC_S, (unsigned)rows * 8u + zs);
         bulk_commit();
         bulk_wait_read0();
       } else {
@@ -442,11 +454,16 @@ __global__ void __launch_bounds__(THREADS, 2)
   const int c0 = warp * (BN / 8);
   const int mine = max(0, min(BN / 8, cols - c0));
   if (lane == 0 && !(PROBE & 2)) {
-    mbar_arrive_expect_tx(bar, (unsigned)(rows * mine) * 8u);
+    // generic-proxy reads of the stages (all warps, ordered by the barrier) before the async-proxy writes below.
+    // Without this fence the copies were seen to land while slower warps were still multiplying the last k-tiles
+    // (BAR.SYNC.DEFER_BLOCKING holds back dependent memory instructions, not the bulk-copy issue).
+    const unsigned z = after_barrier_zero(bar);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_arrive_expect_tx(bar, (unsigned)(rows * mine) * 8u + z);
     const double* src = C + (int64_t)(n0 + c0) * ldc + m0;
 #pragma unroll
     for (int c = 0; c < BN / 8; ++c)
-      if (c < mine) bulk_g2s(Cs + (c0 + c) * LDC_S, src + (int64_t)c * ldc, (unsigned)rows * 8u, bar);
+      if (c < mine) bulk_g2s(Cs + (c0 + c) * LDC_S, src + (int64_t)c * ldc, (unsigned)rows * 8u + z, bar);
   }
   __syncwarp();
   if (!(PROBE & 2)) mbar_wait(bar, 0);
@@ -463,13 +480,247 @@ __global__ void __launch_bounds__(THREADS, 2)
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
   if (lane == 0 && (!(PROBE & 1) || m < 0)) {
+    const unsigned zs = after_barrier_zero(Cs);  // every warp's C - P is in the buffer before any column leaves
     double* dst = C + (int64_t)(n0 + c0) * ldc + m0;
 #pragma unroll
     for (int c = 0; c < BN / 8; ++c)
-      if (c < mine) bulk_s2g(dst + (int64_t)c * ldc, Cs + (c0 + c) * LDC_S, (unsigned)rows * 8u);
+      if (c < mine) bulk_s2g(dst + (int64_t)c * ldc, Cs + (c0 + c) * LDC_S, (unsigned)rows * 8u + zs);
     bulk_commit();
     bulk_wait_read0();
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-tile kernel with A and B fed by the tensor-map TMA as well.  No thread computes a load address, there is no
+// LDGSTS and no CTA barrier in the main loop:
+//   * 4 stages of 24 KB: A k-tile = 8 boxes of 16 (m) x 16 (k) doubles, B k-tile = one box of 16 (k) x 64 (n), both with
+//     the 128-byte swizzle (rows of 128 B; the 16-byte chunk index is XORed with the row index mod 8), landing on a
+//     "full" mbarrier per stage (expect_tx = 24 576 B).  9 UTMALDG per k-tile, issued by lane 0 of warp (kt mod 8),
+//     two k-tiles ahead, after an "empty" mbarrier (8 arrivals: every warp, after its last LDS of the stage's
+//     previous use) -- with 4 stages and a prefetch distance of 2 that wait is over before it starts;
+//   * bank-conflict-free fragment loads from the dense swizzled tiles need the four k of one DMMA to differ in
+//     ((k & 7) >> 1) [A: 4 k-rows x 4 consecutive m per half-warp] and in (k & 1, k >> 3) [B: 4 k x 4 n-rows]:
+//     the k of a k-tile are dealt to the four DMMA groups as {0,3,12,15} ^ x, x = 0, 1, 4, 5 (any assignment of
+//     the summation index to DMMA slots is valid as long as A and B use the same one).  A thread's 8 + 4 fragment
+//     addresses are then TA0 ^ (144 x) ^ (64 (f & 1)) + 2048 (f >> 1) and TB0 ^ (8 x) + 1024 g: two registers
+//     and compile-time constants;
+//   * C as in dgemm_sub_tma_kernel (bulk copies into the freed stages, C - P in place, bulk stores).
+// ---------------------------------------------------------------------------------------
+constexpr int T2_STAGES = 4;
+constexpr int T2_A_BYTES = BM * BK * 8, T2_B_BYTES = BN * BK * 8, T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
+constexpr size_t T2_SMEM_BYTES = 1024 + (size_t)T2_STAGES * T2_STAGE_BYTES + 128;
+static_assert((size_t)C_STAGE * sizeof(double) <= (size_t)T2_STAGES * T2_STAGE_BYTES, "the C tile must fit into the stages");
+
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <int PROBE>
+__global__ void __launch_bounds__(THREADS, 2)
+    dgemm_sub_tma2_kernel(const CUtensorMap* __restrict__ maps, int m, int n, int k, double* __restrict__ C, int64_t ldc,
+                          const int* __restrict__ fail, int dep) {
+  // maps[0] = A, maps[1] = B in global memory (a ring of slots in the context, written by a stream-ordered copy)
+  const CUtensorMap& mapA = maps[0];
+  const CUtensorMap& mapB = maps[1];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // 1024: the CTA's window itself must sit on a swizzle-pattern boundary
+  const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned sbase = (raw + 1023u) & ~1023u;  // the swizzle pattern is a function of the absolute address
+  unsigned char* sgen = smem_raw + (sbase - raw);
+  uint64_t* bars = (uint64_t*)(sgen + T2_STAGES * T2_STAGE_BYTES);  // full[4], empty[4], cbar
+  const unsigned bar0 = sbase + T2_STAGES * T2_STAGE_BYTES;
+  const bool poisoned = lu_poisoned(lu_failword(fail), dep);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int KT = k / BK;
+  const int rows = min(BM, m - m0), cols = min(BN, n - n0);
+
+  auto produce = [&](int kt) {  // one thread: the 9 boxes of k-tile kt
+    const int st = kt & (T2_STAGES - 1);
+    const unsigned fb = bar0 + 8u * st;
+    const unsigned dst = sbase + st * T2_STAGE_BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"((unsigned)T2_STAGE_BYTES) : "memory");
+#pragma unroll
+    for (int j = 0; j < BM / 16; ++j) tma_load_2d(dst + j * 2048, &mapA, m0 + 16 * j, kt * BK, fb);
+    tma_load_2d(dst + T2_A_BYTES, &mapB, kt * BK, n0, fb);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < T2_STAGES; ++i) {
+      mbar_init(&bars[i], 1);
+      mbar_init(&bars[T2_STAGES + i], 8);
+    }
+    mbar_init(&bars[2 * T2_STAGES], 8);
+    mbar_init(&bars[2 * T2_STAGES + 1], 8);
+    mbar_init(&bars[2 * T2_STAGES + 2], 8);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (!(PROBE & 8)) {
+      produce(0);
+      if (KT > 1) produce(1);
+      if ((PROBE & 16) && KT > 2) produce(2);
+    }
+  }
+  __syncthreads();
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc[f][g][0] = acc[f][g][1] = 0.0;
+
+  {  // my own C tile -> L2 (64 columns x 8 lines of 128 B): the loads after the main loop then hit L2
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int line = tid + q * THREADS;
+      const int col = line >> 3, row = (line & 7) * 16;
+      if (col < cols && row < rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (int64_t)(n0 + col) * ldc + m0 + row));
+    }
+  }
+
+  const int rr = lane >> 2, kq = lane & 3;
+  const int kp = (kq & 1) * 3 + (kq >> 1) * 12;  // this lane's k in DMMA group 0: {0, 3, 12, 15}
+  const unsigned ta0 = (unsigned)(wm * 2) * 2048u + kp * 128u + ((((rr >> 1) ^ kp) & 7) << 4) + (rr & 1) * 8u;
+  const unsigned tb0 = T2_A_BYTES + (unsigned)(wn * 32 + rr) * 128u + ((((kp >> 1) ^ rr) & 7) << 4) + (kp & 1) * 8u;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int cs = kt & (T2_STAGES - 1);
+    if (!(PROBE & 8)) mbar_wait(&bars[cs], (kt / T2_STAGES) & 1);
+    if (PROBE & 16) {
+      // CTA barrier per k-tile: everybody is done with k-tile kt - 1, whose stage takes k-tile kt + 3
+      __syncthreads();
+      if (warp == (kt & 7) && lane == 0 && kt + 3 < KT && !(PROBE & 8)) produce(kt + 3);
+    } else if (warp == (kt & 7) && lane == 0 && kt + 2 < KT && !(PROBE & 8)) {
+      const int nx = kt + 2;
+      if (nx >= T2_STAGES) mbar_wait(&bars[T2_STAGES + (nx & (T2_STAGES - 1))], (nx / T2_STAGES - 1) & 1);
+      produce(nx);
+    }
+    __syncwarp();
+    const unsigned char* st = sgen + cs * T2_STAGE_BYTES;
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      constexpr int xs[4] = {0, 1, 4, 5};
+      const unsigned xa = xs[gi] * 144u, xb = xs[gi] * 8u;
+      double af[4], bf[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        af[f] = *(const double*)(st + ((ta0 ^ xa ^ ((f & 1) * 64u)) + (f >> 1) * 2048u));
+#pragma unroll
+      for (int g = 0; g < 4; ++g) bf[g] = *(const double*)(st + ((tb0 ^ xb) + g * 1024u));
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dmma884(acc[f][g][0], acc[f][g][1], af[f], bf[g]);
+    }
+    if (!(PROBE & 16)) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[T2_STAGES + cs]);
+    }
+  }
+  if (poisoned) return;
+  if (PROBE & 32) {  // direct epilogue (debugging): C - P through the LSU
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int gm = m0 + wm * 32 + 8 * f + (lane >> 2);
+      if (gm >= m) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gn = n0 + wn * 32 + 8 * g + 2 * (lane & 3) + e;
+          if (gn < n) C[(int64_t)gn * ldc + gm] -= acc[f][g][e];
+        }
+    }
+    return;
+  }
+  // every warp is done with the stages: they become the C tile (columns of LDC_S doubles)
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&bars[2 * T2_STAGES + 1]);
+  mbar_wait(&bars[2 * T2_STAGES + 1], 0);
+  double* Cs = (double*)sgen;
+  uint64_t* cbar = &bars[2 * T2_STAGES];
+  const int c0 = warp * (BN / 8);
+  const int mine = max(0, min(BN / 8, cols - c0));
+  if (PROBE & 64) {  // C tile by coalesced 16-byte loads (thread t: rows 2 (t % 64), 2 (t % 64) + 1 of columns t / 64 + 4 i)
+    const int r = 2 * (tid & 63), cq = tid >> 6;
+    double2 v[BN / 4];
+#pragma unroll
+    for (int i2 = 0; i2 < BN / 4; ++i2) {
+      const int c = cq + 4 * i2;
+      v[i2] = (r < rows && c < cols) ? __ldcs((const double2*)(C + (int64_t)(n0 + c) * ldc + m0 + r)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int i2 = 0; i2 < BN / 4; ++i2) *(double2*)(Cs + (cq + 4 * i2) * LDC_S + r) = v[i2];
+    __syncthreads();
+  }
+  if (lane == 0 && !(PROBE & 2) && !(PROBE & 64)) {
+    const unsigned z = after_barrier_zero(cbar);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // (see dgemm_sub_tma_kernel)
+    mbar_arrive_expect_tx(cbar, (unsigned)(rows * mine) * 8u + z);
+    const double* src = C + (int64_t)(n0 + c0) * ldc + m0;
+#pragma unroll
+    for (int c = 0; c < BN / 8; ++c)
+      if (c < mine) bulk_g2s(Cs + (c0 + c) * LDC_S, src + (int64_t)c * ldc, (unsigned)rows * 8u + z, cbar);
+  }
+  __syncwarp();
+  if (!(PROBE & 2) && !(PROBE & 64)) mbar_wait(cbar, 0);
+  double* cb = Cs + (wn * 32 + 2 * (lane & 3)) * LDC_S + wm * 32 + (lane >> 2);
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      double* cp = cb + (8 * g) * LDC_S + 8 * f;
+      const double t0 = cp[0], t1 = cp[LDC_S];
+      cp[0] = t0 - acc[f][g][0];
+      cp[LDC_S] = t1 - acc[f][g][1];
+    }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&bars[2 * T2_STAGES + 2]);
+  mbar_wait(&bars[2 * T2_STAGES + 2], 0);
+  if (lane == 0 && (!(PROBE & 1) || m < 0)) {
+    const unsigned zs = after_barrier_zero(Cs);  // every warp's C - P is in the buffer before any column leaves
+    double* dst = C + (int64_t)(n0 + c0) * ldc + m0;
+#pragma unroll
+    for (int c = 0; c < BN / 8; ++c)
+      if (c < mine) bulk_s2g(dst + (int64_t)c * ldc, Cs + (c0 + c) * LDC_S, (unsigned)rows * 8u + zs);
+    bulk_commit();
+    bulk_wait_read0();
+  }
+}
+
+// Host side: tensor maps of the operands of one product.  A: m x k column-major (lda), boxes of 16 x 16; B: k x n
+// column-major (ldb), boxes of 16 x 64; both FP64, 128-byte swizzle, out-of-bounds elements read as zero.
+typedef CUresult (*mmr_tmap_encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline mmr_tmap_encode_t mmr_tmap_encoder() {
+  static mmr_tmap_encode_t fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (mmr_tmap_encode_t)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+inline bool mmr_tmap_2d(CUtensorMap* map, const double* base, uint64_t inner, uint64_t outer, int64_t ld, uint32_t box_inner,
+                        uint32_t box_outer) {
+  mmr_tmap_encode_t enc = mmr_tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t es[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace mmr_gemm

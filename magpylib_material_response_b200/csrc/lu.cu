@@ -868,6 +868,32 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }
+  // MMR_DGEMM_TMA2 = 1: the tensor-map kernel with the barrier-free main loop (dgemm_sub_tma2_kernel: 34.9 TF at
+  // k = 256 against 33.9).  OFF by default: inside the LU with look-ahead it produced factors that were wrong by one
+  // k-tile's worth of products in a few tiles (4 runs of 5; never in isolation) -- see the notes in dgemm_tma.cuh.
+  static int tma2_on = -1;
+  if (tma2_on < 0) {
+    const char* e = getenv("MMR_DGEMM_TMA2");
+    tma2_on = e ? atoi(e) : 0;
+  }
+  if (tma_ok && tma2_on && tma_min_tiles > 0 && ntiles >= tma_min_tiles) {
+    constexpr unsigned TMAP_SLOTS = 4096;
+    if (!ctx->tmap_ring) MMR_CUDA(cudaMalloc(&ctx->tmap_ring, (size_t)TMAP_SLOTS * 2 * sizeof(CUtensorMap)));
+    alignas(64) CUtensorMap maps[2];
+    if (mmr_tmap_2d(&maps[0], A, (uint64_t)m, (uint64_t)k, lda, 16, 16) && mmr_tmap_2d(&maps[1], B, (uint64_t)k, (uint64_t)n, ldb, 16, BN)) {
+      CUtensorMap* slot = (CUtensorMap*)ctx->tmap_ring + 2 * (size_t)(ctx->tmap_next++ % TMAP_SLOTS);
+      // (pageable source: the runtime stages the 256 bytes before it returns, so `maps` may go out of scope)
+      MMR_CUDA(cudaMemcpyAsync(slot, maps, sizeof(maps), cudaMemcpyHostToDevice, s));
+      auto kern = dgemm_sub_tma2_kernel<0>;
+      if (tma2_on == 2) kern = dgemm_sub_tma2_kernel<16>;  // CTA barrier per k-tile
+      if (tma2_on == 3) kern = dgemm_sub_tma2_kernel<32>;  // direct C - P epilogue
+      if (tma2_on == 4) kern = dgemm_sub_tma2_kernel<64>;  // C tile by coalesced generic loads
+      if ((arc = mmr_func_smem(ctx, (const void*)kern, T2_SMEM_BYTES))) return arc;
+      kern<<<grid, THREADS, T2_SMEM_BYTES, s>>>(slot, (int)m, (int)n, (int)k, C, ldc, fail, dep);
+      MMR_CHECK_LAUNCH(ctx);
+      return 0;
+    }
+  }
   if (tma_ok && tma_min_tiles > 0 && ntiles >= tma_min_tiles) {
     auto kern = dgemm_sub_tma_kernel<0>;
     if ((arc = mmr_func_smem(ctx, (const void*)kern, T_SMEM_BYTES))) return arc;
