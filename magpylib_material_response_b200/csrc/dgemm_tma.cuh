@@ -505,6 +505,14 @@ __global__ void __launch_bounds__(THREADS, 2)
 //     addresses are then TA0 ^ (144 x) ^ (64 (f & 1)) + 2048 (f >> 1) and TB0 ^ (8 x) + 1024 g: two registers
 //     and compile-time constants;
 //   * C as in dgemm_sub_tma_kernel (bulk copies into the freed stages, C - P in place, bulk stores).
+// A stage is released (arrive on its "empty" mbarrier) at the TOP of the following iteration, behind the wait loop
+// of the next k-tile, never at the end of its own iteration: there ptxas schedules the arrive in front of the last
+// 24 DMMAs, where the fragment loads that feed them may still be queued, and the producer's next TMA box can then
+// land under them.  Alone on the GPU that never showed; inside the LU, with the look-ahead kernels competing for
+// the LSU, it corrupted a few half-tiles per factorization by one k-tile's worth of products (4 runs of 5).  Behind
+// the wait loop every DMMA of the released k-tile has been issued, so its operands have arrived (in-order issue).
+// PROBE: 1 = no output, 2 = no C input, 8 = no loads (timing probes, wrong results); 16 = CTA barrier per k-tile
+// instead of the empty barriers (33.4 TF), 32 = direct C - P epilogue, 64 = C tile by coalesced generic loads.
 // ---------------------------------------------------------------------------------------
 constexpr int T2_STAGES = 4;
 constexpr int T2_A_BYTES = BM * BK * 8, T2_B_BYTES = BN * BK * 8, T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
@@ -589,6 +597,13 @@ __global__ void __launch_bounds__(THREADS, 2)
   for (int kt = 0; kt < KT; ++kt) {
     const int cs = kt & (T2_STAGES - 1);
     if (!(PROBE & 8)) mbar_wait(&bars[cs], (kt / T2_STAGES) & 1);
+    // Release the stage of k-tile kt - 1 only now, behind the wait loop: every DMMA of that k-tile has been issued
+    // (in-order issue), so every LDS that fed them has returned.  At the end of iteration kt - 1 ptxas moves the
+    // arrive up in front of the last 24 DMMAs, i.e. to a point where the last fragment loads may still be in flight.
+    if (!(PROBE & 16) && kt > 0) {
+      if (lane == 0) mbar_arrive(&bars[T2_STAGES + ((kt - 1) & (T2_STAGES - 1))]);
+      __syncwarp();
+    }
     if (PROBE & 16) {
       // CTA barrier per k-tile: everybody is done with k-tile kt - 1, whose stage takes k-tile kt + 3
       __syncthreads();
@@ -614,10 +629,6 @@ __global__ void __launch_bounds__(THREADS, 2)
       for (int f = 0; f < 4; ++f)
 #pragma unroll
         for (int g = 0; g < 4; ++g) dmma884(acc[f][g][0], acc[f][g][1], af[f], bf[g]);
-    }
-    if (!(PROBE & 16)) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[T2_STAGES + cs]);
     }
   }
   if (poisoned) return;

@@ -868,13 +868,12 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     MMR_CHECK_LAUNCH(ctx);
     return 0;
   }
-  // MMR_DGEMM_TMA2 = 1: the tensor-map kernel with the barrier-free main loop (dgemm_sub_tma2_kernel: 34.9 TF at
-  // k = 256 against 33.9).  OFF by default: inside the LU with look-ahead it produced factors that were wrong by one
-  // k-tile's worth of products in a few tiles (4 runs of 5; never in isolation) -- see the notes in dgemm_tma.cuh.
+  // MMR_DGEMM_TMA2 (default 1): the tensor-map kernel with the barrier-free main loop (dgemm_sub_tma2_kernel, 34.8 TF
+  // at k = 256); 0: A / B by cp.async (dgemm_sub_tma_kernel, 33.9 TF); 2 / 3 / 4: variants kept for A/B timing.
   static int tma2_on = -1;
   if (tma2_on < 0) {
     const char* e = getenv("MMR_DGEMM_TMA2");
-    tma2_on = e ? atoi(e) : 0;
+    tma2_on = e ? atoi(e) : 1;
   }
   if (tma_ok && tma2_on && tma_min_tiles > 0 && ntiles >= tma_min_tiles) {
     constexpr unsigned TMAP_SLOTS = 4096;
