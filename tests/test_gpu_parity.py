@@ -294,6 +294,57 @@ def test_dgemm_dmma_vs_fp64_reference(ctx, m, n, k):
     assert torch.all(dC[:, m:] == 0)  # padding untouched
 
 
+@pytest.mark.parametrize(("m", "n", "k"), [(2048, 1280, 256), (2000, 1400, 256), (4102, 2050, 48), (2304, 2112, 16),
+                                         (2001, 1400, 64)])
+def test_dgemm_tma_kernels_vs_fp64_reference(ctx, m, n, k):
+    """C -= A B on grids of at least one full wave (296 tiles of 128 x 64): the TMA kernels of dgemm_tma.cuh --
+    A / B by tensor-map loads, C by bulk copies through shared memory -- with ragged last tiles in m and n;
+    an odd m must fall back to the cp.async kernel (bulk copies move multiples of 16 bytes)."""
+    rng = np.random.default_rng(m + n + k)
+    lda, ldb, ldc = m + 2 + (m % 2), k + 4, m + 6 + (m % 2)
+    dA = torch.zeros(k, lda, dtype=torch.float64, device=ctx.device)
+    dA[:, :m] = torch.from_numpy(rng.normal(size=(k, m))).to(ctx.device)
+    dB = torch.zeros(n, ldb, dtype=torch.float64, device=ctx.device)
+    dB[:, :k] = torch.from_numpy(rng.normal(size=(n, k))).to(ctx.device)
+    dC = torch.zeros(n, ldc, dtype=torch.float64, device=ctx.device)
+    dC[:, :m] = torch.from_numpy(rng.normal(size=(n, m))).to(ctx.device)
+    P = dB[:, :k] @ dA[:, :m]  # (column-major views: (A B)^T = B^T A^T)
+    ref = dC[:, :m] - 2.0 * P
+    for _ in range(2):  # two updates in a row
+        ctx.dgemm_nn(m, n, k, -1.0, dA, lda, dB, ldb, 1.0, dC, ldc)
+    ctx.sync()
+    torch.testing.assert_close(dC[:, :m], ref, rtol=1e-12, atol=1e-12 * np.sqrt(k))
+    assert torch.all(dC[:, m:] == 0)  # padding untouched
+
+
+@pytest.mark.parametrize("N", [5184, 6400])
+def test_lu_speculative_with_lookahead_is_reproducible(ctx, N):
+    """Diagonally dominant system (speculative panels, deferred TRSM, look-ahead on a second stream: the demag code
+    path) at a size where the trailing updates run on the barrier-free tensor-map kernel.  The factorization is
+    repeated: every run must give the same bits and a residual at rounding level.  (A stage of that kernel released
+    too early showed up exactly here: residual 1e-8 in 4 runs of 5, different every time.)"""
+    g = torch.Generator(device=ctx.device)
+    g.manual_seed(N)
+    ld = (N + 15) // 16 * 16
+    Q0 = torch.randn(N, ld, dtype=torch.float64, device=ctx.device, generator=g) * (0.5 / N)
+    Q0[:, :N] += torch.eye(N, dtype=torch.float64, device=ctx.device)
+    b = torch.randn(N, dtype=torch.float64, device=ctx.device, generator=g)
+    first = None
+    for _ in range(4):
+        Q = Q0.clone()
+        x = b.clone()
+        ipiv = torch.zeros(N, dtype=torch.int32, device=ctx.device)
+        assert ctx.lu_factor(Q, ld, ipiv) == 0
+        ctx.lu_solve(Q, ld, ipiv, x)
+        ctx.sync()
+        r = Q0[:, :N] @ x - b  # (the rows of the buffer are the rows of Q; the LU works on the column-major view Q^T)
+        assert float(torch.linalg.norm(r) / torch.linalg.norm(b)) < 1e-13
+        if first is None:
+            first = Q
+        else:
+            assert torch.equal(Q, first)
+
+
 @pytest.mark.parametrize("N", [1, 5, 16, 130, 777, 1000, 2049])
 def test_lu_solve_random_dense_vs_numpy(ctx, N):
     """General (non diagonally dominant) matrices: partial pivoting is required."""
