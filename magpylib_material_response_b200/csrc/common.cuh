@@ -64,9 +64,6 @@ struct mmr_ctx {
   bool panel_reg_ok = false;                           // non-portable cluster sizes allowed for the register strips
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // third stream + events of the distributed LU: broadcasts run beside the panel chain
-  // ring of tensor-map pairs in device memory for the TMA-fed GEMM (lu.cu: mmr_dgemm_launch)
-  void* tmap_ring = nullptr;
-  unsigned tmap_next = 0;
   cudaStream_t comm = nullptr;
   cudaStream_t aux = nullptr;  // low priority: deferred work of the single-GPU LU (U12 rows finalised off the critical path)
   cudaEvent_t evd[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

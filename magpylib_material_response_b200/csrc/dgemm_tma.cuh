@@ -527,11 +527,8 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 
 template <int PROBE>
 __global__ void __launch_bounds__(THREADS, 2)
-    dgemm_sub_tma2_kernel(const CUtensorMap* __restrict__ maps, int m, int n, int k, double* __restrict__ C, int64_t ldc,
-                          const int* __restrict__ fail, int dep) {
-  // maps[0] = A, maps[1] = B in global memory (a ring of slots in the context, written by a stream-ordered copy)
-  const CUtensorMap& mapA = maps[0];
-  const CUtensorMap& mapB = maps[1];
+    dgemm_sub_tma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int m, int n, int k,
+                          double* __restrict__ C, int64_t ldc, const int* __restrict__ fail, int dep) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // 1024: the CTA's window itself must sit on a swizzle-pattern boundary
   const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
   const unsigned sbase = (raw + 1023u) & ~1023u;  // the swizzle pattern is a function of the absolute address

@@ -876,19 +876,14 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
     tma2_on = e ? atoi(e) : 1;
   }
   if (tma_ok && tma2_on && tma_min_tiles > 0 && ntiles >= tma_min_tiles) {
-    constexpr unsigned TMAP_SLOTS = 4096;
-    if (!ctx->tmap_ring) MMR_CUDA(cudaMalloc(&ctx->tmap_ring, (size_t)TMAP_SLOTS * 2 * sizeof(CUtensorMap)));
-    alignas(64) CUtensorMap maps[2];
-    if (mmr_tmap_2d(&maps[0], A, (uint64_t)m, (uint64_t)k, lda, 16, 16) && mmr_tmap_2d(&maps[1], B, (uint64_t)k, (uint64_t)n, ldb, 16, BN)) {
-      CUtensorMap* slot = (CUtensorMap*)ctx->tmap_ring + 2 * (size_t)(ctx->tmap_next++ % TMAP_SLOTS);
-      // (pageable source: the runtime stages the 256 bytes before it returns, so `maps` may go out of scope)
-      MMR_CUDA(cudaMemcpyAsync(slot, maps, sizeof(maps), cudaMemcpyHostToDevice, s));
+    alignas(64) CUtensorMap mapA, mapB;  // passed by value (__grid_constant__ parameters)
+    if (mmr_tmap_2d(&mapA, A, (uint64_t)m, (uint64_t)k, lda, 16, 16) && mmr_tmap_2d(&mapB, B, (uint64_t)k, (uint64_t)n, ldb, 16, BN)) {
       auto kern = dgemm_sub_tma2_kernel<0>;
       if (tma2_on == 2) kern = dgemm_sub_tma2_kernel<16>;  // CTA barrier per k-tile
       if (tma2_on == 3) kern = dgemm_sub_tma2_kernel<32>;  // direct C - P epilogue
       if (tma2_on == 4) kern = dgemm_sub_tma2_kernel<64>;  // C tile by coalesced generic loads
       if ((arc = mmr_func_smem(ctx, (const void*)kern, T2_SMEM_BYTES))) return arc;
-      kern<<<grid, THREADS, T2_SMEM_BYTES, s>>>(slot, (int)m, (int)n, (int)k, C, ldc, fail, dep);
+      kern<<<grid, THREADS, T2_SMEM_BYTES, s>>>(mapA, mapB, (int)m, (int)n, (int)k, C, ldc, fail, dep);
       MMR_CHECK_LAUNCH(ctx);
       return 0;
     }
