@@ -185,6 +185,14 @@ int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, co
                  int64_t lda, const double* d_B, int64_t ldb, double beta, double* d_C,
                  int64_t ldc);
 
+/* B (nb0 + nb1 rows x ncols, COLUMN-major, ld ldb, in place) <- L_blk^-1 B for the unit-lower two-panel block
+ * L_blk = [L00 0; L10 L11], given L00^-1 (nb0 x nb0, ld nb0), L11^-1 (nb1 x nb1, ld nb1) and L10 (nb1 x nb0, ld ldl):
+ * the U12 step of the blocked LU (the triangular solve inside LAPACK dgetrf behind np.linalg.solve, demag.py:470)
+ * as ONE launch.  nb0 = 128, 0 < nb1 <= 128 with nb1 % 16 == 0, 16-byte aligned operands, even leading dimensions;
+ * exported for tests. */
+int mmr_block_trsm(mmr_ctx* ctx, int nb0, int nb1, const double* d_Linv0, const double* d_Linv1, const double* d_L10,
+                   int64_t ldl, double* d_B, int64_t ldb, int ncols);
+
 /* ---- kernel 2b: restarted GMRES on the same Q with iterative-refinement check ----------- */
 /*
  * Solves Q x = b (row-major Q, ld).  x holds the initial guess on entry.  Stops when the TRUE

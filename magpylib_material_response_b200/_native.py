@@ -97,6 +97,11 @@ _SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, _c_double_p,
          ctypes.c_int64, _c_double_p, ctypes.c_int64, ctypes.c_double, _c_double_p, ctypes.c_int64],
     ),
+    "mmr_block_trsm": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, ctypes.c_int64, _c_double_p,
+         ctypes.c_int64, ctypes.c_int],
+    ),
     "mmr_gmres": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p,
@@ -368,6 +373,11 @@ class Context:
     def dgemm_nn(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
         _check(self.lib, self.lib.mmr_dgemm_nn(self.handle, m, n, k, alpha, _ptr(A), lda, _ptr(B), ldb,
                                                beta, _ptr(C), ldc))
+
+    def block_trsm(self, nb0, nb1, Linv0, Linv1, L10, ldl, B, ldb, ncols):
+        """B <- [L00 0; L10 L11]^-1 B in one launch (column-major operands, see include/mmr_b200.h)."""
+        _check(self.lib, self.lib.mmr_block_trsm(self.handle, nb0, nb1, _ptr(Linv0), _ptr(Linv1), _ptr(L10), ldl,
+                                                 _ptr(B), ldb, ncols))
 
     # ---- kernel 2b -------------------------------------------------------------------
     def gmres(self, Q, ld, b, x, tol=1e-10, restart=200, maxit=2000, raise_on_fail=True):

@@ -20,6 +20,7 @@
 #include "comm.h"
 #include "dgemm.cuh"
 #include "dgemm_tma.cuh"
+#include "block_trsm.cuh"
 #include "panel128.cuh"
 
 namespace cg = cooperative_groups;
@@ -910,6 +911,41 @@ int mmr_dgemm_launch(mmr_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t
   return 0;
 }
 
+// B (nb0 + nb1 rows, ncols columns, in place) <- L_blk^-1 B in one launch (block_trsm.cuh).  Returns -2 when the
+// shapes / alignments are not the ones the kernel is written for (the caller then issues the three products).
+int mmr_block_trsm_launch(mmr_ctx* ctx, cudaStream_t s, int nb0, int nb1, const double* Linv0, const double* Linv1,
+                          const double* L10, int64_t ldl, double* B, int64_t ldb, int ncols, int* fail, int dep) {
+  using namespace mmr_gemm;
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MMR_LU_BLOCK_TRSM");  // 0: three launches (round-2 start)
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on || nb0 != BM || nb1 <= 0 || nb1 > BM || nb1 % BK != 0 || ncols <= 0 || ldl % 2 != 0 || ldb % 2 != 0 ||
+      (((uintptr_t)Linv0 | (uintptr_t)Linv1 | (uintptr_t)L10 | (uintptr_t)B) % 16) != 0)
+    return -2;
+  int arc = mmr_func_smem(ctx, (const void*)lu_block_trsm_kernel, BT_SMEM_BYTES);
+  if (arc) return arc;
+  const int ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, s);
+  lu_block_trsm_kernel<<<(unsigned)ceil_div64(ncols, BT_COLS), THREADS, BT_SMEM_BYTES, s>>>(nb0, nb1, Linv0, Linv1, L10, ldl, B, ldb,
+                                                                                          ncols, fail, dep);
+  MMR_CHECK_LAUNCH(ctx);
+  mmr_prof_end(ctx, ps, (2.0 * nb0 * nb0 + 2.0 * nb1 * nb0 + 2.0 * nb1 * nb1) * (double)ncols, s);
+  return 0;
+}
+
+extern "C" int mmr_block_trsm(mmr_ctx* ctx, int nb0, int nb1, const double* d_Linv0, const double* d_Linv1, const double* d_L10,
+                              int64_t ldl, double* d_B, int64_t ldb, int ncols) {
+  MMR_ARG(ctx != nullptr, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  const int r = mmr_block_trsm_launch(ctx, ctx->stream, nb0, nb1, d_Linv0, d_Linv1, d_L10, ldl, d_B, ldb, ncols, nullptr, 0);
+  if (r == -2) {
+    mmr_set_error("mmr_block_trsm: unsupported shape or alignment");
+    return -1;
+  }
+  return r;
+}
+
 extern "C" int mmr_dgemm_nn(mmr_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
                             const double* d_A, int64_t lda, const double* d_B, int64_t ldb,
                             double beta, double* d_C, int64_t ldc) {
@@ -1336,6 +1372,8 @@ __global__ void lu_fill_ipiv_kernel(int* __restrict__ p0, int* __restrict__ p1, 
 }
 
 }  // namespace
+
+constexpr int BLOCK_TRSM_MAX_COLS = 512;  // wider ranges keep the three full-grid products
 
 size_t mmr_lu_spec_scratch_bytes() { return sizeof(double) * NB * NB + 256; }  // U11^-1
 
@@ -2115,19 +2153,30 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
     return laswp(s, kb, k1, pslot(kb, 1), -1, k1);  // panel 1's interchanges on panel 0's columns
   };
   // trailing update of the column range [cb, ce) by the outer block [kb, kb+ob)
-  auto update_cols = [&](int kb, int ob, int cb, int ce) -> int {
+  auto update_cols_on = [&](cudaStream_t us, int kind_big, int kb, int ob, int cb, int ce) -> int {
     if (ce <= cb) return 0;
     const int nb0 = min(NB, ob), nb1 = ob - nb0;
     const int dep = last_panel(kb);
-    int r = laswp(main_s, cb, ce, pslot(kb, 0), nb1 > 0 ? pslot(kb, 1) : -1, dep);
+    int r = laswp(us, cb, ce, pslot(kb, 0), nb1 > 0 ? pslot(kb, 1) : -1, dep);
     if (r) return r;
-    if ((r = trsm(main_s, Linv(kb, 0), kb, nb0, cb, ce, dep))) return r;
-    if (nb1 > 0) {
-      if ((r = gemm(main_s, MMR_PROF_TRSM, kb + nb0, kb + ob, kb, nb0, cb, ce, dep))) return r;
-      if ((r = trsm(main_s, Linv(kb, 1), kb + nb0, nb1, cb, ce, dep))) return r;
+    // narrow column ranges (the look-ahead update): the three U12 steps in one launch
+    bool fused = false;
+    if (nb1 > 0 && ce - cb <= BLOCK_TRSM_MAX_COLS) {
+      r = mmr_block_trsm_launch(ctx, us, nb0, nb1, Linv(kb, 0), Linv(kb, 1), A + (int64_t)kb * ld + kb + nb0, ld,
+                                A + (int64_t)cb * ld + kb, ld, ce - cb, d_fail, dep);
+      if (r == 0) fused = true;
+      else if (r != -2) return r;
     }
-    return gemm(main_s, MMR_PROF_GEMM, kb + ob, N, kb, ob, cb, ce, dep);
+    if (!fused) {
+      if ((r = trsm(us, Linv(kb, 0), kb, nb0, cb, ce, dep))) return r;
+      if (nb1 > 0) {
+        if ((r = gemm(us, MMR_PROF_TRSM, kb + nb0, kb + ob, kb, nb0, cb, ce, dep))) return r;
+        if ((r = trsm(us, Linv(kb, 1), kb + nb0, nb1, cb, ce, dep))) return r;
+      }
+    }
+    return gemm(us, kind_big, kb + ob, N, kb, ob, cb, ce, dep);
   };
+  auto update_cols = [&](int kb, int ob, int cb, int ce) -> int { return update_cols_on(main_s, MMR_PROF_GEMM, kb, ob, cb, ce); };
   // Look-ahead (depth 1): as soon as the columns of outer block k+1 have received the update of
   // block k, block k+1 is factored on the high-priority side stream while the main stream applies
   // the rest of update k.  The two touch disjoint column ranges.
@@ -2175,6 +2224,11 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   };
   // One pass over the outer blocks from kb0 on.  Entry state: everything left of kb0 is factored and applied,
   // block kb0 has received all earlier updates (and, with first_inner = 1, its panel 0 is done).
+  static int narrow_side_on = -1;
+  if (narrow_side_on < 0) {
+    const char* e = getenv("MMR_LU_NARROW_SIDE");  // 0: the narrow update stays on the main stream (round-2 start)
+    narrow_side_on = (e && e[0] == '0') ? 0 : 1;
+  }
   auto run = [&](int kb0, int first_inner) -> int {
     int r = factor_outer(main_s, kb0, min(OB, N - kb0), first_inner);
     if (r) return r;
@@ -2196,7 +2250,18 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
         if ((r = build_W(kb, par))) return r;
         MMR_CUDA(cudaEventRecord(e_W[par], cm_s));
       }
-      if ((r = update_cols(kb, ob, next, cb2))) return r;
+      // The narrow update of the next block's columns: with W it does not feed the big GEMM of this iteration (other
+      // columns), only the factorization of the next block -- so it goes to the high-priority side stream in front of
+      // that factorization and the main stream runs one big GEMM behind the other (it used to sit between them:
+      // ~0.2 ms of a nearly idle GPU per block).  e_it: everything queued on the main stream so far, i.e. the previous
+      // big GEMM (which updated these columns) and the wait for this block's factorization.
+      const bool narrow_on_side = use_W && lookahead && narrow_side_on;
+      if (narrow_on_side) {
+        MMR_CUDA(cudaStreamWaitEvent(side_s, e_it, 0));
+        if ((r = update_cols_on(side_s, MMR_PROF_PANEL_GEMM, kb, ob, next, cb2))) return r;
+      } else {
+        if ((r = update_cols(kb, ob, next, cb2))) return r;
+      }
       if (lookahead) {
         MMR_CUDA(cudaEventRecord(ctx->ev[0], main_s));
         if (use_W) {
@@ -2598,13 +2663,21 @@ extern "C" int mmr_lu_factor_dist(mmr_ctx* ctx, int64_t N64, int64_t nrows_local
       if (r) return r;
       mmr_prof_end(ctx, ps, 32.0 * ob * (double)(c1 - c0), st);
     }
-    if ((r = trsm(st, LinvOf(s, 0), nb0, B, c1 - c0, dep))) return r;
-    if (nb1 > 0) {
-      ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
-      r = mmr_dgemm_launch(ctx, st, nb1, c1 - c0, nb0, -1.0, P + nb0, m, B, ld, 1.0, B + nb0, ld, d_fail, dep);
-      if (r) return r;
-      mmr_prof_end(ctx, ps, 2.0 * nb1 * (double)(c1 - c0) * nb0, st);
-      if ((r = trsm(st, LinvOf(s, 1), nb1, B + nb0, c1 - c0, dep))) return r;
+    bool fused = false;
+    if (nb1 > 0 && c1 - c0 <= BLOCK_TRSM_MAX_COLS) {  // (the look-ahead update of my next block: one launch)
+      r = mmr_block_trsm_launch(ctx, st, nb0, nb1, LinvOf(s, 0), LinvOf(s, 1), P + nb0, m, B, ld, c1 - c0, d_fail, dep);
+      if (r == 0) fused = true;
+      else if (r != -2) return r;
+    }
+    if (!fused) {
+      if ((r = trsm(st, LinvOf(s, 0), nb0, B, c1 - c0, dep))) return r;
+      if (nb1 > 0) {
+        ps = mmr_prof_begin(ctx, MMR_PROF_TRSM, st);
+        r = mmr_dgemm_launch(ctx, st, nb1, c1 - c0, nb0, -1.0, P + nb0, m, B, ld, 1.0, B + nb0, ld, d_fail, dep);
+        if (r) return r;
+        mmr_prof_end(ctx, ps, 2.0 * nb1 * (double)(c1 - c0) * nb0, st);
+        if ((r = trsm(st, LinvOf(s, 1), nb1, B + nb0, c1 - c0, dep))) return r;
+      }
     }
     if (m > ob) {
       ps = mmr_prof_begin(ctx, MMR_PROF_GEMM, st);

@@ -317,6 +317,32 @@ def test_dgemm_tma_kernels_vs_fp64_reference(ctx, m, n, k):
     assert torch.all(dC[:, m:] == 0)  # padding untouched
 
 
+@pytest.mark.parametrize(("nb1", "ncols"), [(128, 256), (112, 240), (64, 37), (128, 512)])
+def test_block_trsm_one_launch_vs_triangular_solve(ctx, nb1, ncols):
+    """U12 = L_blk^-1 A12 for a two-panel block in one launch (block_trsm.cuh) against a triangular solve."""
+    nb0 = 128
+    ob = nb0 + nb1
+    g = torch.Generator(device=ctx.device)
+    g.manual_seed(nb1 * 1000 + ncols)
+    L = torch.tril(torch.randn(ob, ob, dtype=torch.float64, device=ctx.device, generator=g) * 0.05, -1)  # (well conditioned)
+    L += torch.eye(ob, dtype=torch.float64, device=ctx.device)
+    Bm = torch.randn(ob, ncols, dtype=torch.float64, device=ctx.device, generator=g)
+    ref = torch.linalg.solve_triangular(L, Bm, upper=False, unitriangular=True)
+    # column-major operands = transposed row-major torch tensors
+    Linv0 = torch.linalg.inv(L[:nb0, :nb0]).T.contiguous()
+    Linv1 = torch.linalg.inv(L[nb0:, nb0:]).T.contiguous()
+    ldl = ob + 6
+    L10 = torch.zeros(nb0, ldl, dtype=torch.float64, device=ctx.device)
+    L10[:, :nb1] = L[nb0:, :nb0].T
+    ldb = ob + 10
+    Bc = torch.full((ncols + 3, ldb), 7.0, dtype=torch.float64, device=ctx.device)
+    Bc[:ncols, :ob] = Bm.T
+    ctx.block_trsm(nb0, nb1, Linv0, Linv1, L10, ldl, Bc, ldb, ncols)
+    ctx.sync()
+    torch.testing.assert_close(Bc[:ncols, :ob].T, ref, rtol=1e-12, atol=1e-12 * float(ref.abs().max()))
+    assert torch.all(Bc[ncols:] == 7.0) and torch.all(Bc[:, ob:] == 7.0)  # nothing outside the block was touched
+
+
 @pytest.mark.parametrize("N", [5184, 6400])
 def test_lu_speculative_with_lookahead_is_reproducible(ctx, N):
     """Diagonally dominant system (speculative panels, deferred TRSM, look-ahead on a second stream: the demag code
