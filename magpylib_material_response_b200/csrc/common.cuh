@@ -66,7 +66,7 @@ struct mmr_ctx {
   // third stream + events of the distributed LU: broadcasts run beside the panel chain
   cudaStream_t comm = nullptr;
   cudaStream_t aux = nullptr;  // low priority: deferred work of the single-GPU LU (U12 rows finalised off the critical path)
-  cudaEvent_t evd[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evd[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 void mmr_set_error(const char* fmt, ...);

@@ -197,7 +197,7 @@ extern "C" int mmr_ctx_create(int device, void* stream, mmr_ctx** out) {
     c->lookahead = !(la && la[0] == '0');
   }
   for (int i = 0; i < 4; ++i) MMR_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
-  for (int i = 0; i < 8; ++i) MMR_CUDA(cudaEventCreateWithFlags(&c->evd[i], cudaEventDisableTiming));
+  for (int i = 0; i < 10; ++i) MMR_CUDA(cudaEventCreateWithFlags(&c->evd[i], cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -219,7 +219,7 @@ extern "C" int mmr_ctx_destroy(mmr_ctx* ctx) {
   if (ctx->hpin) cudaFreeHost(ctx->hpin);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 10; ++i)
     if (ctx->evd[i]) cudaEventDestroy(ctx->evd[i]);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->comm) cudaStreamDestroy(ctx->comm);

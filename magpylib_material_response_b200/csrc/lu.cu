@@ -2063,7 +2063,7 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   const bool defer_trsm = spec_on && ctx->lookahead && defer_default && OB == 2 * NB && N > 4 * OB;
   const size_t wbuf_bytes = defer_trsm ? ((sizeof(double) * (size_t)N * OB + 255) / 256 * 256) : 0;
   const size_t tbuf_bytes = defer_trsm ? ((sizeof(double) * (size_t)N * NB + 255) / 256 * 256) : 0;
-  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 4 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes + stash_bytes +
+  int rc = mmr_ws_reserve(ctx, 256 + scratch_bytes + 8 * sizeof(double) * NB * NB + spec_bytes + sbuf_bytes + stash_bytes +
                                    2 * wbuf_bytes + tbuf_bytes);
   if (rc) return rc;
   rc = mmr_hpin_reserve(ctx, 256);
@@ -2072,14 +2072,16 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   int* d_fail = d_info + 1;
   void* scratch = (char*)ctx->ws + 256;
   double* Lbuf = (double*)((char*)ctx->ws + 256 + scratch_bytes);
-  void* d_spec = (char*)Lbuf + 4 * sizeof(double) * NB * NB;
+  void* d_spec = (char*)Lbuf + 8 * sizeof(double) * NB * NB;
   double* Sbuf = (double*)((char*)d_spec + spec_bytes);
   double* stash = (double*)((char*)Sbuf + sbuf_bytes);
   double* Wbuf[2] = {(double*)((char*)stash + stash_bytes), (double*)((char*)stash + stash_bytes + wbuf_bytes)};
   double* Tbuf = (double*)((char*)stash + stash_bytes + 2 * wbuf_bytes);
   auto slot_of = [&](int kb) { return stash + (size_t)(2 * (kb / OB) + ((kb % OB) ? 1 : 0)) * 2 * NB * NB; };
   // inverse of the unit-lower diagonal block of inner panel `inner` of the outer block at kb
-  auto Linv = [&](int kb, int inner) { return Lbuf + (size_t)((((kb / OB) & 1) << 1) + inner) * NB * NB; };
+  // (four generations of the pair: the deferred U12 work of block kb - 2 OB still reads its inverses while block
+  // kb + OB is being factored -- with two generations the factorization had to wait for it)
+  auto Linv = [&](int kb, int inner) { return Lbuf + (size_t)((((kb / OB) & 3) << 1) + inner) * NB * NB; };
   MMR_CUDA(cudaMemsetAsync(d_info, 0, 2 * sizeof(int), ctx->stream));
   double* A = d_Q;
   cudaStream_t main_s = ctx->stream;
@@ -2193,8 +2195,9 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   // low-priority stream, concurrently with the next block's GEMM.
   cudaStream_t cm_s = ctx->comm, aux_s = ctx->aux;
   cudaEvent_t e_it = ctx->evd[0], e_W[2] = {ctx->evd[1], ctx->evd[2]}, e_bulk[2] = {ctx->evd[3], ctx->evd[4]},
-              e_trsm[2] = {ctx->evd[5], ctx->evd[6]}, e_join = ctx->evd[7];
+              e_trsm[4] = {ctx->evd[5], ctx->evd[6], ctx->evd[8], ctx->evd[9]}, e_join = ctx->evd[7];
   bool par_used[2] = {false, false};
+  bool trsm_used[4] = {false, false, false, false};  // e_trsm[g]: the deferred U12 work that read inverse generation g
   auto build_W = [&](int kb, int par) -> int {  // on cm_s; block [kb, kb + 2 NB) is factored and committed
     const int m = N - kb - OB, mW = m, dep = kb + NB;
     double* W = Wbuf[par];
@@ -2224,6 +2227,11 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
   };
   // One pass over the outer blocks from kb0 on.  Entry state: everything left of kb0 is factored and applied,
   // block kb0 has received all earlier updates (and, with first_inner = 1, its panel 0 is done).
+  static int w_early_on = -1;
+  if (w_early_on < 0) {
+    const char* e = getenv("MMR_LU_W_EARLY");  // 0: W waits for the previous big GEMM (round-2 start)
+    w_early_on = (e && e[0] == '0') ? 0 : 1;
+  }
   static int narrow_side_on = -1;
   if (narrow_side_on < 0) {
     const char* e = getenv("MMR_LU_NARROW_SIDE");  // 0: the narrow update stays on the main stream (round-2 start)
@@ -2245,7 +2253,12 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
       if (use_W) {
         // W of this block on the communication stream, beside the narrow update below
         MMR_CUDA(cudaEventRecord(e_it, main_s));
-        MMR_CUDA(cudaStreamWaitEvent(cm_s, e_it, 0));
+        // W needs this block's factorization (ev[1], recorded on the side stream in the previous iteration) and its
+        // buffer, NOT the previous big GEMM: waiting for e_it here (everything queued on the main stream) put the three
+        // W products between two big GEMMs -- 0.15-0.2 ms of a nearly idle GPU per block, 17.7 ms of a 281 ms
+        // factorization (tools/lu_single_timeline.py).  First block of a pass: factored on the main stream, so e_it.
+        if (lookahead && kb != kb0 && w_early_on) MMR_CUDA(cudaStreamWaitEvent(cm_s, ctx->ev[1], 0));
+        else MMR_CUDA(cudaStreamWaitEvent(cm_s, e_it, 0));
         if (par_used[par]) MMR_CUDA(cudaStreamWaitEvent(cm_s, e_bulk[par], 0));  // the GEMM that read this W buffer
         if ((r = build_W(kb, par))) return r;
         MMR_CUDA(cudaEventRecord(e_W[par], cm_s));
@@ -2275,14 +2288,15 @@ extern "C" int mmr_lu_factor(mmr_ctx* ctx, int64_t N64, double* d_Q, int64_t ld,
           MMR_CUDA(cudaEventRecord(e_bulk[par], main_s));
           MMR_CUDA(cudaStreamWaitEvent(aux_s, e_bulk[par], 0));
           if ((r = finish_U12(aux_s, kb, cb2, N))) return r;
-          MMR_CUDA(cudaEventRecord(e_trsm[par], aux_s));
+          MMR_CUDA(cudaEventRecord(e_trsm[(kb / OB) & 3], aux_s));
+          trsm_used[(kb / OB) & 3] = true;
           par_used[par] = true;
         } else {
           if ((r = update_cols(kb, ob, cb2, N))) return r;
         }
         MMR_CUDA(cudaStreamWaitEvent(side_s, ctx->ev[0], 0));
-        // the L11^-1 buffers of block `next` are those of block kb - OB: its deferred U12 rows must be done
-        if (par_used[par ^ 1]) MMR_CUDA(cudaStreamWaitEvent(side_s, e_trsm[par ^ 1], 0));
+        // the L11^-1 buffers of block `next` are those of block next - 4 OB: its deferred U12 rows must be done
+        if (trsm_used[(next / OB) & 3]) MMR_CUDA(cudaStreamWaitEvent(side_s, e_trsm[(next / OB) & 3], 0));
         if ((r = factor_outer(side_s, next, ob2, 0))) return r;
         MMR_CUDA(cudaEventRecord(ctx->ev[1], side_s));
         MMR_CUDA(cudaStreamWaitEvent(main_s, ctx->ev[1], 0));
